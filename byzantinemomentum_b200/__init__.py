@@ -1,0 +1,22 @@
+# coding: utf-8
+"""byzantinemomentum_b200 — B200-native (sm_100a) Byzantine-robust gradient aggregation.
+
+A drop-in for the aggregation hot path of LPD-EPFL/ByzantineMomentum (`aggregators/*.py` as
+called from `attack.py:821-822`): same plugin interface, hand-written CUDA underneath.
+
+    from byzantinemomentum_b200 import gars
+    aggregated = gars["krum"](gradients=list_of_flat_fp32_cuda_tensors, f=5)
+
+    import aggregators                              # the unmodified reference
+    byzantinemomentum_b200.plugin.install(aggregators)   # registers "b200-<name>" rules
+
+Importing this package never touches CUDA; the compiled library is loaded on first use and
+its absence is an error (no CPU fallback).
+"""
+
+from . import _lib, engine, gars as _gars, plugin
+from .gars import gars, make_gar, register, UserException, last_selection
+from .engine import config
+
+__all__ = ["gars", "make_gar", "register", "UserException", "last_selection", "config", "engine", "plugin"]
+__version__ = "0.1.0"

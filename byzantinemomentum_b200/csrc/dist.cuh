@@ -1,0 +1,50 @@
+// dist.cuh — internal interface of the distance-based rules: K2 (pairwise squared
+// distances), K2' (row-to-centre squared distances), K5 (scoring / selection) and K4
+// (Bulyan reduce).  Workspace layout is private to the library.
+#pragma once
+
+#include "common.cuh"
+
+namespace bz {
+
+// ---- workspace ---------------------------------------------------------------------------
+// [0, kWsHeader)                       : int32 scratch (order / selection / status when the
+//                                        caller passes NULL for them)
+// [kWsHeader, kWsHeader + n*n*8)       : reduced block (double[n*n] or double[n])
+// [.., + kMaxParts * n*n*8)            : per-CTA partial blocks of K2 / K2'
+constexpr size_t kWsHeader = 1024;
+constexpr int    kMaxParts = 160;     // >= number of CTAs K2 / K2' ever launch along x
+size_t workspace_bytes(int n);
+
+struct Workspace {
+  int32_t* order;     // n entries
+  int32_t* status;    // 1 entry
+  double*  block;     // n*n
+  double*  parts;     // kMaxParts * n*n
+};
+bool carve_workspace(void* ws, size_t bytes, int n, Workspace& out);
+
+// ---- K2: partial squared pairwise distances -------------------------------------------------
+// parts[x*n*n + i*n + j] (i < j) = this CTA's share of sum_k (rows[i][k] - rows[j][k])^2.
+// Returns the number of partial blocks written (grid size along x), <= kMaxParts.
+int launch_pairdist(const RowTable& rows, int n, int64_t d, double* parts, cudaStream_t st);
+
+// K2': parts[x*n + i] = share of sum_k (rows[i][k] - center[k])^2 (center NULL: the origin).
+int launch_rowdist(const RowTable& rows, int n, const float* center, int64_t d, double* parts, cudaStream_t st);
+
+// Sum `nparts` blocks of `len` doubles in index order into `block` (fixed order: deterministic).
+// pair_n > 0: the block is a pair_n x pair_n table of which only entries i < j are defined; the
+// others are written as 0.
+void launch_reduce_parts(const double* parts, int nparts, int len, int pair_n, double* block, cudaStream_t st);
+
+// ---- K5: scoring / selection (single CTA each) --------------------------------------------------
+void launch_krum_select(const double* parts, int nparts, int n, int f, int32_t* order, cudaStream_t st);
+void launch_bulyan_select(const double* parts, int nparts, int n, int f, int m, int32_t* order, int32_t* status, cudaStream_t st);
+int  launch_brute_select(const double* parts, int nparts, int n, int f, int32_t* sel, int32_t* status, cudaStream_t st);
+void launch_rowdist_select(const double* parts, int nparts, int n, int sqrt_norm, int32_t* order, cudaStream_t st);
+
+// ---- K4: Bulyan stage 1 means + coordinate-wise averaged median ----------------------------------
+bool launch_bulyan_reduce(const RowTable& rows, int n, int f, int m, const int32_t* order, const int32_t* status,
+                          const Span& span, float* out, cudaStream_t st);
+
+}  // namespace bz

@@ -1,0 +1,82 @@
+// k1_inst.cu — instantiations of the K1 kernels for a range of n, compiled once per part
+// (`-DBZ_PART=<0..7>`) so that the 256 kernels build in parallel.  Parts 0-3: k1_median for
+// n in 1-16 / 17-32 / 33-48 / 49-64; parts 4-7: k1_sorted for the same ranges.
+#include "k1_select.cuh"
+#include "launch.cuh"
+
+#ifndef BZ_PART
+#error "compile with -DBZ_PART=<0..7>"
+#endif
+
+#if (BZ_PART % 4) == 0
+#define BZ_N_LIST X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
+#elif (BZ_PART % 4) == 1
+#define BZ_N_LIST X(17) X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26) X(27) X(28) X(29) X(30) X(31) X(32)
+#elif (BZ_PART % 4) == 2
+#define BZ_N_LIST X(33) X(34) X(35) X(36) X(37) X(38) X(39) X(40) X(41) X(42) X(43) X(44) X(45) X(46) X(47) X(48)
+#else
+#define BZ_N_LIST X(49) X(50) X(51) X(52) X(53) X(54) X(55) X(56) X(57) X(58) X(59) X(60) X(61) X(62) X(63) X(64)
+#endif
+
+namespace bz {
+
+static inline unsigned blocks_for(int64_t threads) {
+  return (unsigned)((threads + kK1Threads - 1) / kK1Threads);
+}
+
+#if BZ_PART < 4
+
+template <int N>
+static void launch_median_n(int vec, const RowTable& rows, const Span& span, float* out, cudaStream_t st) {
+  const int64_t threads = span.cnt0 + span.cnt1;
+  if (threads <= 0) return;
+  if (vec == 1) k1_median<N, 1><<<blocks_for(threads), kK1Threads, 0, st>>>(rows, span, out);
+  else          k1_median<N, body_vec(N)><<<blocks_for(threads), kK1Threads, 0, st>>>(rows, span, out);
+}
+
+#define BZ_FN2(p) launch_median_part##p
+#define BZ_FN(p) BZ_FN2(p)
+bool BZ_FN(BZ_PART)(int n, int vec, const RowTable& rows, const Span& span, float* out, cudaStream_t st) {
+  switch (n) {
+#define X(N) case N: launch_median_n<N>(vec, rows, span, out, st); return true;
+    BZ_N_LIST
+#undef X
+    default: return false;
+  }
+}
+
+#else
+
+template <int N, int VEC>
+static void launch_sorted_nv(const RowTable& rows, const Span& span, int mode, int f, float* out, cudaStream_t st) {
+  const int64_t threads = span.cnt0 + span.cnt1;
+  if (threads <= 0) return;
+  size_t smem = 0;
+  if (mode != kModeTrmean) {
+    smem = (size_t)N * VEC * kK1Threads * sizeof(float);
+    static unsigned long long opted = 0;   // per instantiation, one bit per device
+    opt_in_smem(k1_sorted<N, VEC>, smem, opted);
+  }
+  k1_sorted<N, VEC><<<blocks_for(threads), kK1Threads, smem, st>>>(rows, span, mode, f, out);
+}
+
+template <int N>
+static void launch_sorted_n(int vec, const RowTable& rows, const Span& span, int mode, int f, float* out, cudaStream_t st) {
+  if (vec == 1) launch_sorted_nv<N, 1>(rows, span, mode, f, out, st);
+  else          launch_sorted_nv<N, body_vec(N)>(rows, span, mode, f, out, st);
+}
+
+#define BZ_FN2(p) launch_sorted_part##p
+#define BZ_FN(p) BZ_FN2(p)
+bool BZ_FN(BZ_PART)(int n, int vec, const RowTable& rows, const Span& span, int mode, int f, float* out, cudaStream_t st) {
+  switch (n) {
+#define X(N) case N: launch_sorted_n<N>(vec, rows, span, mode, f, out, st); return true;
+    BZ_N_LIST
+#undef X
+    default: return false;
+  }
+}
+
+#endif
+
+}  // namespace bz

@@ -1,0 +1,361 @@
+// k2_pairdist.cu — K2: all n(n-1)/2 squared pairwise distances in ONE pass over the rows
+// (the reference makes n(n-1)/2 passes of `x.sub(y).norm().item()`, each with a host sync:
+// krum.py:44-48, bulyan.py:49-54, brute.py:44-45), and K2': squared distance of every row to
+// a centre vector (cge.py:36, aksel.py:41).
+//
+// K2 layout: persistent CTAs (one per SM) walk tiles of T coordinates.  A tile of all n rows
+// is staged in shared memory with cp.async (zero-filled past d), double buffered.  Rows are
+// grouped by 5; a warp owns one group pair (A, B) — a 5x5 block of row pairs (10 pairs on
+// the diagonal) — and sweeps the tile: each lane reads 4 adjacent coordinates of the 10 rows
+// (LDS.128, conflict free) and feeds 25 packed accumulators with FADD2/FFMA2 (sub.f32x2 /
+// fma.rn.f32x2: two coordinates per instruction).  No Gram trick: (a-b)^2 is formed
+// directly, so aliased rows give an exact 0 and nothing cancels.
+// Every tile (<= 1024 coordinates, i.e. <= 16 terms per fp32 accumulator half) the 25 lane
+// partials are transposed-reduced over the warp (lane p ends with pair p) and added to a
+// per-lane fp64 accumulator; per-CTA fp64 blocks are summed in fixed order by K5.
+// Every pair walks the coordinates in the same lane/step pattern, so identical data (aliased
+// rows) give bitwise identical sums.
+// Roofline: HBM n·4 B per coordinate; secondary: FP32 pipe, n(n-1) lane-ops per coordinate.
+#include "dist.cuh"
+
+namespace bz {
+
+typedef unsigned long long u64;
+
+constexpr int kG = 5;
+constexpr int kK2Warps = 16;
+constexpr int kK2Threads = kK2Warps * 32;
+constexpr int kStep = 128;              // coordinates per warp step (4 per lane)
+constexpr size_t kK2SmemBudget = 226 * 1024;
+
+__device__ __forceinline__ void cp_async16(float* smem, const float* gmem, int src_bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* smem, const float* gmem, int src_bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(K) : "memory"); }
+
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+  u64 d;
+  asm("sub.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float half_sum(u64 v) {
+  return __fadd_rn(__uint_as_float((unsigned)(v & 0xffffffffull)), __uint_as_float((unsigned)(v >> 32)));
+}
+
+// Stage tile [base, base+T) of every row into buf[n][T]; zero fill past d.
+__device__ __forceinline__ void stage_tile(float* buf, const RowTable& rows, int n, int T, int logq,
+                                           int64_t base, int64_t d) {
+  const int total = n << logq;            // 16-byte chunks: n * T/4
+  for (int q = threadIdx.x; q < total; q += kK2Threads) {
+    const int r = q >> logq, cq = q & ((1 << logq) - 1);
+    const float* row = rows.p[r];
+    const int64_t col = base + (int64_t)cq * 4;
+    const int64_t remain = d - col;
+    float* dst = buf + r * T + cq * 4;
+    if ((((uintptr_t)row) & 15) == 0) {
+      const int bytes = remain >= 4 ? 16 : (remain > 0 ? (int)remain * 4 : 0);
+      cp_async16(dst, bytes ? row + col : row, bytes);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int bytes = remain > e ? 4 : 0;
+        cp_async4(dst + e, bytes ? row + col + e : row, bytes);
+      }
+    }
+  }
+}
+
+template <bool DIAG>
+__device__ __forceinline__ void sweep_tile(const float* buf, int T, const int (&oa)[kG], const int (&ob)[kG],
+                                           int lane, u64 (&acc)[kG * kG]) {
+  for (int c = lane * 4; c < T; c += kStep) {
+    u64 a0[kG], a1[kG], b0[kG], b1[kG];
+#pragma unroll
+    for (int i = 0; i < kG; ++i) {
+      const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(buf + oa[i] + c);
+      a0[i] = t.x; a1[i] = t.y;
+    }
+    if (!DIAG) {
+#pragma unroll
+      for (int j = 0; j < kG; ++j) {
+        const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(buf + ob[j] + c);
+        b0[j] = t.x; b1[j] = t.y;
+      }
+#pragma unroll
+      for (int i = 0; i < kG; ++i)
+#pragma unroll
+        for (int j = 0; j < kG; ++j) {
+          const u64 d0 = sub2(a0[i], b0[j]), d1 = sub2(a1[i], b1[j]);
+          acc[i * kG + j] = fma2(d0, d0, acc[i * kG + j]);
+          acc[i * kG + j] = fma2(d1, d1, acc[i * kG + j]);
+        }
+    } else {
+      int p = 0;
+#pragma unroll
+      for (int i = 0; i < kG; ++i)
+#pragma unroll
+        for (int j = i + 1; j < kG; ++j) {
+          const u64 d0 = sub2(a0[i], a0[j]), d1 = sub2(a1[i], a1[j]);
+          acc[p] = fma2(d0, d0, acc[p]);
+          acc[p] = fma2(d1, d1, acc[p]);
+          ++p;
+        }
+    }
+  }
+}
+
+// Transposed warp reduction: on return, lane L holds sum over lanes of v[L] (v has 32 slots).
+__device__ __forceinline__ float transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int j = 0; j < h; ++j) {
+      const float send = up ? v[j] : v[j + h];
+      const float keep = up ? v[j + h] : v[j];
+      v[j] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, h));
+    }
+  }
+  return v[0];
+}
+
+template <int NP>
+__device__ __forceinline__ void flush(u64 (&acc)[kG * kG], int lane, double& dacc) {
+  float v[32];
+#pragma unroll
+  for (int p = 0; p < 32; ++p) v[p] = (p < NP) ? half_sum(acc[p]) : 0.f;
+#pragma unroll
+  for (int p = 0; p < kG * kG; ++p) acc[p] = 0ull;
+  dacc += (double)transpose_reduce(v, lane);
+}
+
+__global__ void __launch_bounds__(kK2Threads, 1)
+k2_pairdist(const __grid_constant__ RowTable rows, const int n, const int T, const int logq, const int64_t d,
+            const int64_t ntiles, double* __restrict__ parts) {
+  extern __shared__ __align__(16) float smem[];   // [2][n][T]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ng = (n + kG - 1) / kG;
+  const int ntasks = ng * (ng + 1) / 2;
+  int task = blockIdx.y * kK2Warps + warp;
+  const bool active = task < ntasks;
+  int ga = 0, gb = 0;
+  if (active) {
+    int t = task;
+    while (t >= ng - ga) { t -= ng - ga; ++ga; }
+    gb = ga + t;
+  }
+  const bool diag = ga == gb;
+  int oa[kG], ob[kG];
+#pragma unroll
+  for (int i = 0; i < kG; ++i) {
+    oa[i] = min(ga * kG + i, n - 1) * T;
+    ob[i] = min(gb * kG + i, n - 1) * T;
+  }
+  u64 acc[kG * kG];
+#pragma unroll
+  for (int p = 0; p < kG * kG; ++p) acc[p] = 0ull;
+  double dacc = 0.;
+
+  const int stage_floats = n * T;
+  int64_t tile = blockIdx.x;
+  if (tile < ntiles) stage_tile(smem, rows, n, T, logq, tile * T, d);
+  cp_async_commit();
+  int cur = 0;
+  for (; tile < ntiles; tile += gridDim.x) {
+    const int64_t next = tile + gridDim.x;
+    if (next < ntiles) stage_tile(smem + (cur ^ 1) * stage_floats, rows, n, T, logq, next * T, d);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    if (active) {
+      const float* buf = smem + cur * stage_floats;
+      if (diag) { sweep_tile<true>(buf, T, oa, ob, lane, acc); flush<10>(acc, lane, dacc); }
+      else      { sweep_tile<false>(buf, T, oa, ob, lane, acc); flush<kG * kG>(acc, lane, dacc); }
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  cp_async_wait<0>();
+
+  if (active) {
+    int i, j;
+    bool valid;
+    if (diag) {
+      // lane p -> p-th pair (i < j) of the group, row-major: (0,1..4) (1,2..4) (2,3..4) (3,4)
+      i = (lane >= 9) ? 3 : (lane >= 7) ? 2 : (lane >= 4) ? 1 : 0;
+      const int first = (i == 0) ? 0 : (i == 1) ? 4 : (i == 2) ? 7 : 9;
+      j = lane - first + i + 1;
+      valid = lane < 10;
+    } else {
+      i = lane / kG; j = lane % kG;
+      valid = lane < kG * kG;
+    }
+    const int ri = ga * kG + i, rj = gb * kG + j;
+    if (valid && ri < n && rj < n) parts[(size_t)blockIdx.x * n * n + (size_t)ri * n + rj] = dacc;
+  }
+}
+
+// ---- K2': squared distance of every row to a centre --------------------------------------------
+// Warp w of a CTA owns rows w, w+16, w+32, w+48; lanes stride over the CTA's coordinates with
+// float4 loads straight from global memory (no reuse to stage).  fp32 partials over <= 32
+// terms, then per-lane fp64.
+constexpr int kRdThreads = 512;
+constexpr int kRdRows = (kMaxN + 15) / 16;   // rows per warp
+
+template <bool CENTER, int VEC>
+__global__ void __launch_bounds__(kRdThreads)
+k2_rowdist(const __grid_constant__ RowTable rows, const int n, const float* __restrict__ center,
+           const int64_t base, const int64_t nvec, double* __restrict__ parts) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double dacc[kRdRows];
+#pragma unroll
+  for (int k = 0; k < kRdRows; ++k) dacc[k] = 0.;
+  // A CTA walks chunks of 32 lanes * 8 vectors; all 16 warps of the CTA visit the same chunk
+  // (the centre is shared through L1), each on its own rows.
+  const int64_t chunk = 32 * 8;
+  for (int64_t v0 = (int64_t)blockIdx.x * chunk; v0 < nvec; v0 += (int64_t)gridDim.x * chunk) {
+    float acc[kRdRows];
+#pragma unroll
+    for (int k = 0; k < kRdRows; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int64_t iv = v0 + u * 32 + lane;
+      if (iv < nvec) {
+        const int64_t e = base + iv * VEC;
+        float c[VEC];
+        if (CENTER) VecLoad<VEC>::load(center + e, c);
+#pragma unroll
+        for (int k = 0; k < kRdRows; ++k) {
+          const int r = warp + 16 * k;
+          if (r < n) {
+            float x[VEC];
+            VecLoad<VEC>::load(rows.p[r] + e, x);
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) {
+              // aksel.py:41 `(x - m).pow_(2).sum()`: the square is rounded to fp32, then summed;
+              // cge.py:36 `norm()`: sum of squares, fused
+              if (CENTER) {
+                const float df = __fsub_rn(x[q], c[q]);
+                acc[k] = __fadd_rn(acc[k], __fmul_rn(df, df));
+              } else {
+                acc[k] = fmaf(x[q], x[q], acc[k]);
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kRdRows; ++k) dacc[k] += (double)acc[k];
+  }
+#pragma unroll
+  for (int k = 0; k < kRdRows; ++k) {
+    double v = dacc[k];
+#pragma unroll
+    for (int h = 16; h >= 1; h >>= 1) v += __shfl_xor_sync(0xffffffffu, v, h);
+    const int r = warp + 16 * k;
+    if (lane == 0 && r < n) parts[(size_t)blockIdx.x * n + r] = v;
+  }
+}
+
+// ---- fixed-order reduction of partial blocks --------------------------------------------------
+__global__ void k_reduce_parts(const double* __restrict__ parts, int nparts, int len, int pair_n, double* __restrict__ block) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= len) return;
+  if (pair_n > 0 && (e / pair_n) >= (e % pair_n)) { block[e] = 0.; return; }
+  double s = 0.;
+  for (int p = 0; p < nparts; ++p) s += parts[(size_t)p * len + e];
+  block[e] = s;
+}
+
+// ---- host side ---------------------------------------------------------------------------
+
+static int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& c = cached[dev & 63];
+  if (c == 0) cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev);
+  return c > 0 ? c : 148;
+}
+
+int launch_pairdist(const RowTable& rows, int n, int64_t d, double* parts, cudaStream_t st) {
+  // Largest power-of-two tile whose two stages fit the shared memory of one CTA per SM
+  int T = 1024;
+  while (T > 128 && (size_t)2 * n * T * sizeof(float) > kK2SmemBudget) T >>= 1;
+  int logq = 0;
+  while ((1 << logq) < T / 4) ++logq;
+  const size_t smem = (size_t)2 * n * T * sizeof(float);
+  static unsigned long long opted = 0;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(opted & bit)) {
+      cudaFuncSetAttribute(k2_pairdist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK2SmemBudget);
+      opted |= bit;
+    }
+  }
+  const int ng = (n + kG - 1) / kG;
+  const int ntasks = ng * (ng + 1) / 2;
+  const int gy = (ntasks + kK2Warps - 1) / kK2Warps;
+  const int64_t ntiles = (d + T - 1) / T;
+  int gx = sm_count() / (gy > 0 ? gy : 1);
+  if (gx < 1) gx = 1;
+  if (gx > kMaxParts) gx = kMaxParts;
+  if ((int64_t)gx > ntiles) gx = (int)(ntiles > 0 ? ntiles : 1);
+  k2_pairdist<<<dim3(gx, gy > 0 ? gy : 1), kK2Threads, smem, st>>>(rows, n, T, logq, d, ntiles, parts);
+  return gx;
+}
+
+int launch_rowdist(const RowTable& rows, int n, const float* center, int64_t d, double* parts, cudaStream_t st) {
+  // Vector width: every row (and the centre) must be 16-byte aligned, else scalar loads
+  bool al = true;
+  for (int r = 0; r < n && al; ++r) al = (((uintptr_t)rows.p[r]) & 15) == 0;
+  if (center != nullptr) al = al && ((((uintptr_t)center) & 15) == 0);
+  const int64_t chunk4 = 32 * 8 * 4;
+  int gx = sm_count() * 2;
+  if (gx > kMaxParts) gx = kMaxParts;
+  // Body (vectorised) + scalar tail share one partial layout: the tail is a second launch
+  // that ADDS nothing in place; instead the vector kernel covers floor(d/4)*4 elements and the
+  // scalar kernel the rest, each writing its own range of blocks.
+  const int64_t nvec4 = al ? d / 4 : 0;
+  const int64_t rest = d - nvec4 * 4;
+  int used = 0;
+  if (nvec4 > 0) {
+    int g = gx - 1;
+    const int64_t need = (nvec4 * 4 + chunk4 - 1) / chunk4;
+    if ((int64_t)g > need) g = (int)need;
+    if (g < 1) g = 1;
+    if (center) k2_rowdist<true, 4><<<g, kRdThreads, 0, st>>>(rows, n, center, 0, nvec4, parts);
+    else        k2_rowdist<false, 4><<<g, kRdThreads, 0, st>>>(rows, n, center, 0, nvec4, parts);
+    used = g;
+  }
+  if (rest > 0 || used == 0) {
+    int g = al ? 1 : gx;
+    const int64_t need = (rest + 32 * 8 - 1) / (32 * 8);
+    if ((int64_t)g > need) g = (int)(need > 0 ? need : 1);
+    if (g > kMaxParts - used) g = kMaxParts - used;
+    if (center) k2_rowdist<true, 1><<<g, kRdThreads, 0, st>>>(rows, n, center, nvec4 * 4, rest, parts + (size_t)used * n);
+    else        k2_rowdist<false, 1><<<g, kRdThreads, 0, st>>>(rows, n, center, nvec4 * 4, rest, parts + (size_t)used * n);
+    used += g;
+  }
+  return used;
+}
+
+void launch_reduce_parts(const double* parts, int nparts, int len, int pair_n, double* block, cudaStream_t st) {
+  k_reduce_parts<<<(len + 255) / 256, 256, 0, st>>>(parts, nparts, len, pair_n, block);
+}
+
+}  // namespace bz

@@ -1,0 +1,73 @@
+// k3_average.cu — K3: ordered-subset average,
+//   out[j] = (((z + g[s0][j]) + g[s1][j]) + ... + g[s(c-1)][j]) / divisor
+// with z = 0.0f for Python `sum()` call sites (average.py:29, krum.py:80, brute.py:80,
+// aksel.py:64) or the first row itself for cge.py:53-56; fp32 adds in the given order, one
+// IEEE division — bit-exact with the reference given the same selection.
+// The selection is read from DEVICE memory (written by the K5 scoring kernel), so the
+// distance pass, the scoring and this pass chain on one stream with no host round trip.
+// Roofline: HBM, (count + 1)·4 B per coordinate.
+#include "launch.cuh"
+
+namespace bz {
+
+constexpr int kK3Threads = 256;
+constexpr int kK3Unroll = 8;
+
+template <int VEC>
+__global__ void __launch_bounds__(kK3Threads)
+k3_average(const __grid_constant__ RowTable rows, const Span span, const int32_t* __restrict__ sel,
+           const int count, const int zero_init, const float divisor,
+           const int32_t* __restrict__ status, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * kK3Threads + threadIdx.x;
+  if (i >= span.cnt0 + span.cnt1) return;
+  const int64_t e = span_element<VEC>(span, i);
+  float acc[VEC];
+  if (status != nullptr && *status != 0) {
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) acc[c] = quiet_nan();
+    VecLoad<VEC>::store(out + e, acc);
+    return;
+  }
+  {
+    const int r0 = sel ? sel[0] : 0;
+    float t[VEC];
+    VecLoad<VEC>::load(rows.p[r0] + e, t);
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) acc[c] = zero_init ? __fadd_rn(0.f, t[c]) : t[c];
+  }
+  int k = 1;
+  for (; k + kK3Unroll <= count; k += kK3Unroll) {
+    float t[kK3Unroll][VEC];
+#pragma unroll
+    for (int u = 0; u < kK3Unroll; ++u) {
+      const int r = sel ? sel[k + u] : k + u;
+      VecLoad<VEC>::load(rows.p[r] + e, t[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kK3Unroll; ++u)
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) acc[c] = __fadd_rn(acc[c], t[u][c]);
+  }
+  for (; k < count; ++k) {
+    const int r = sel ? sel[k] : k;
+    float t[VEC];
+    VecLoad<VEC>::load(rows.p[r] + e, t);
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) acc[c] = __fadd_rn(acc[c], t[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) acc[c] = __fdiv_rn(acc[c], divisor);
+  VecLoad<VEC>::store(out + e, acc);
+}
+
+void launch_average(int vec, const RowTable& rows, const Span& span, const int32_t* sel, int count,
+                    int zero_init, float divisor, const int32_t* status, float* out, cudaStream_t st) {
+  const int64_t threads = span.cnt0 + span.cnt1;
+  if (threads <= 0) return;
+  const unsigned blocks = (unsigned)((threads + kK3Threads - 1) / kK3Threads);
+  if (vec == 4)      k3_average<4><<<blocks, kK3Threads, 0, st>>>(rows, span, sel, count, zero_init, divisor, status, out);
+  else if (vec == 2) k3_average<2><<<blocks, kK3Threads, 0, st>>>(rows, span, sel, count, zero_init, divisor, status, out);
+  else               k3_average<1><<<blocks, kK3Threads, 0, st>>>(rows, span, sel, count, zero_init, divisor, status, out);
+}
+
+}  // namespace bz

@@ -1,0 +1,96 @@
+// k4_bulyan.cu — K4: Bulyan's reduce pass, fused per coordinate (bulyan.py:64-84).
+//
+// The reference materialises `selected[theta, d]` (theta = n-2f-2 Multi-Krum means, each a
+// pass over up to m rows), then runs median / topk / take / mean over it.  Here one thread owns
+// one coordinate: it reads the m_max = n-f-2 best-scored rows once (in score order, from the
+// device-side `order` written by K5) into a shared-memory column, forms the theta running
+// means in the reference's left-to-right order, sorts them in registers (NaN last), takes
+// the lower median and averages the beta = theta-2f values closest to it.
+// Scores are never updated between iterations (bulyan.py:74-76 is unreachable), so iteration i
+// averages sorted positions i .. i+m_i-1 with m_i = min(m, m_max - i).
+// Roofline: HBM, (m_max + 1)·4 B per coordinate.
+#include "dist.cuh"
+#include "networks_gen.cuh"
+
+namespace bz {
+
+constexpr int kK4Threads = 128;
+
+template <int THETA>
+__global__ void __launch_bounds__(kK4Threads)
+k4_bulyan(const __grid_constant__ RowTable rows, const Span span, const int n, const int f, const int m,
+          const int32_t* __restrict__ order, const int32_t* __restrict__ status, float* __restrict__ out) {
+  extern __shared__ float sm[];   // [max(m_max, THETA)][kK4Threads]
+  const int64_t i = (int64_t)blockIdx.x * kK4Threads + threadIdx.x;
+  if (i >= span.cnt0 + span.cnt1) return;
+  const int64_t e = span_element<1>(span, i);
+  if (status != nullptr && *status != 0) { out[e] = quiet_nan(); return; }
+  float* col = sm + threadIdx.x;
+  const int m_max = n - f - 2;
+  // The m_max best-scored rows of this coordinate, in score order
+  int k = 0;
+  for (; k + 8 <= m_max; k += 8) {
+    float t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t[u] = __ldcs(rows.p[order[k + u]] + e);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) col[(k + u) * kK4Threads] = t[u];
+  }
+  for (; k < m_max; ++k) col[k * kK4Threads] = __ldcs(rows.p[order[k]] + e);
+  // Stage 1: selected[i] = sum(gradients at sorted positions i..i+m_i-1).div_(m_i)  (bulyan.py:66-70)
+  int key[THETA];
+  int mi = m;
+#pragma unroll
+  for (int it = 0; it < THETA; ++it) {
+    mi = min(mi, m_max - it);
+    float acc = __fadd_rn(0.f, col[it * kK4Threads]);
+    for (int q = 1; q < mi; ++q) acc = __fadd_rn(acc, col[(it + q) * kK4Threads]);
+    key[it] = float_to_key(__fdiv_rn(acc, (float)mi));
+  }
+  // Stage 2 (bulyan.py:78-84): lower median over theta, beta closest to it, mean
+  SortNet<THETA>::template run<OpsKey>(key);
+  float last = key_to_float(key[THETA - 1]);
+  const float med = (last != last) ? quiet_nan() : key_to_float(key[(THETA - 1) / 2]);
+#pragma unroll
+  for (int it = 0; it < THETA; ++it) col[it * kK4Threads] = key_to_float(key[it]);
+  const int beta = THETA - 2 * f;
+  const int R = THETA - beta;
+  int lstar = 0;
+  for (int l = 0; l < R; ++l) {
+    const int dlo = abs_key(__fsub_rn(col[l * kK4Threads], med));
+    const int dhi = abs_key(__fsub_rn(col[(l + beta) * kK4Threads], med));
+    lstar += (dlo > dhi) ? 1 : 0;
+  }
+  float acc = 0.f;
+  for (int q = 0; q < beta; ++q) acc = __fadd_rn(acc, col[(lstar + q) * kK4Threads]);
+  const float r = __fdiv_rn(acc, (float)beta);
+  out[e] = (med != med) ? quiet_nan() : r;
+}
+
+template <int THETA>
+static void launch_theta(const RowTable& rows, const Span& span, int n, int f, int m, const int32_t* order,
+                         const int32_t* status, float* out, cudaStream_t st) {
+  const int64_t threads = span.cnt0 + span.cnt1;
+  if (threads <= 0) return;
+  const int m_max = n - f - 2;
+  const int rowsm = m_max > THETA ? m_max : THETA;
+  const size_t smem = (size_t)rowsm * kK4Threads * sizeof(float);
+  k4_bulyan<THETA><<<(unsigned)((threads + kK4Threads - 1) / kK4Threads), kK4Threads, smem, st>>>(
+      rows, span, n, f, m, order, status, out);
+}
+
+bool launch_bulyan_reduce(const RowTable& rows, int n, int f, int m, const int32_t* order, const int32_t* status,
+                          const Span& span, float* out, cudaStream_t st) {
+  const int theta = n - 2 * f - 2;
+  switch (theta) {
+#define X(T) case T: launch_theta<T>(rows, span, n, f, m, order, status, out, st); return true;
+    X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
+    X(17) X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26) X(27) X(28) X(29) X(30) X(31) X(32)
+    X(33) X(34) X(35) X(36) X(37) X(38) X(39) X(40) X(41) X(42) X(43) X(44) X(45) X(46) X(47) X(48)
+    X(49) X(50) X(51) X(52) X(53) X(54) X(55) X(56) X(57) X(58) X(59) X(60)
+#undef X
+    default: return false;
+  }
+}
+
+}  // namespace bz

@@ -1,0 +1,313 @@
+// k5_score.cu — K5: scoring and selection on the n x n distance table, one CTA, on device.
+// The reference does this part in Python on the host after n(n-1)/2 `.item()` syncs
+// (krum.py:49-62, bulyan.py:56-62, brute.py:47-68, aksel.py:49, cge.py:38); here it chains on
+// the stream between the distance pass and the reduce pass, and must reproduce Python's
+// behaviour exactly: distances are fp32 values widened to double, non-finite -> +inf
+// (krum.py:46-47), `sum()` of floats is CPython's (>= 3.12: Neumaier-compensated), sorts are
+// stable, brute enumerates `itertools.combinations` in lexicographic order with a strict `<`.
+#include <math_constants.h>
+
+#include "dist.cuh"
+
+namespace bz {
+
+constexpr int kK5Threads = 1024;
+
+__device__ __forceinline__ bool finite_d(double x) { return fabs(x) <= 1.7976931348623157e308; }
+
+// Sum `nparts` partial blocks in index order (bitwise reproducible on every rank).
+__device__ __forceinline__ double sum_parts(const double* __restrict__ parts, int nparts, size_t stride, size_t e) {
+  double s = 0.;
+  for (int p = 0; p < nparts; ++p) s += parts[(size_t)p * stride + e];
+  return s;
+}
+
+// dist[i][j] = double(fl32(sqrt(sum_k (x_i - x_j)^2))); diagonal = `diag`.
+__device__ void load_distances(const double* __restrict__ parts, int nparts, int n, bool map_nonfinite, double diag,
+                               double* dist) {
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e - i * n;
+    if (i < j) {
+      double v = (double)(float)sqrt(sum_parts(parts, nparts, (size_t)n * n, e));
+      if (map_nonfinite && !finite_d(v)) v = CUDART_INF;
+      dist[i * n + j] = v;
+      dist[j * n + i] = v;
+    } else if (i == j) {
+      dist[e] = diag;
+    }
+  }
+  __syncthreads();
+}
+
+// CPython >= 3.12 `sum()` over floats (Objects/bltinmodule.c: Neumaier's compensated sum;
+// the compensation is dropped when it is not finite).
+__device__ double py_sum(const double* v, int count) {
+  if (count <= 0) return 0.;
+  double f = v[0], c = 0.;
+  for (int k = 1; k < count; ++k) {
+    const double x = v[k];
+    const double t = f + x;
+    if (fabs(f) >= fabs(x)) c += (f - t) + x;
+    else                    c += (x - t) + f;
+    f = t;
+  }
+  if (c != 0. && finite_d(c)) f += c;
+  return f;
+}
+
+// Row-wise ascending sort by ranking: sorted[i][rank] = dist[i][j] (ties by column index).
+__device__ void sort_rows(const double* dist, double* sorted, int n) {
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e - i * n;
+    const double v = dist[e];
+    int rank = 0;
+    for (int k = 0; k < n; ++k) {
+      const double w = dist[i * n + k];
+      rank += (w < v || (w == v && k < j)) ? 1 : 0;
+    }
+    sorted[i * n + rank] = v;
+  }
+  __syncthreads();
+}
+
+// Stable ascending argsort of key[0..n): order[rank] = index.  NaN keys sort last.
+__device__ void stable_order(const double* key, int n, int32_t* __restrict__ order) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = key[i];
+    const bool vn = v != v;
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const double w = key[j];
+      const bool wn = w != w;
+      const bool less = vn ? (!wn) : (!wn && w < v);
+      const bool same = vn ? wn : (w == v);
+      rank += (less || (same && j < i)) ? 1 : 0;
+    }
+    order[rank] = i;
+  }
+}
+
+// krum.py:52-62 (count = n-f-1, diagonal excluded) and bulyan.py:56-62 (count = m over the
+// row INCLUDING its +inf diagonal).  Putting +inf on the diagonal serves both: the extra +inf
+// can only be reached after every finite distance, where the sum is +inf either way.
+__global__ void __launch_bounds__(kK5Threads)
+k5_score_select(const double* __restrict__ parts, int nparts, int n, int count, int32_t* __restrict__ order,
+                int32_t* __restrict__ status, int f, int m, int bulyan) {
+  extern __shared__ double sm[];
+  double* dist = sm;
+  double* sorted = sm + n * n;
+  double* score = sm + 2 * n * n;
+  load_distances(parts, nparts, n, true, CUDART_INF, dist);
+  sort_rows(dist, sorted, n);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) score[i] = py_sum(sorted + i * n, count);
+  __syncthreads();
+  stable_order(score, n, order);
+  if (threadIdx.x == 0 && status != nullptr) {
+    int st = BZ_STATUS_OK;
+    if (bulyan) {
+      // bulyan.py:65-73: from the second iteration on, pruned `(inf, None)` entries precede every
+      // +inf score (stable sort), so fewer than m_i finite scores left means gradients[None]
+      int finite = 0;
+      for (int i = 0; i < n; ++i) finite += finite_d(score[i]) ? 1 : 0;
+      const int m_max = n - f - 2, theta = n - 2 * f - 2;
+      int mi = m;
+      for (int i = 0; i < theta; ++i) {
+        mi = min(mi, m_max - i);
+        if (i >= 1 && finite - i < mi) st = BZ_STATUS_DEGENERATE;
+      }
+    }
+    *status = st;
+  }
+}
+
+// aksel.py:39-49 / cge.py:28-38: stable order of n keys.
+__global__ void __launch_bounds__(256)
+k5_rowdist_select(const double* __restrict__ parts, int nparts, int n, int sqrt_norm, int32_t* __restrict__ order) {
+  __shared__ double key[kMaxN];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double s = sum_parts(parts, nparts, (size_t)n, i);
+    double v;
+    if (sqrt_norm) {
+      v = (double)(float)sqrt(s);
+      if (!finite_d(v)) v = CUDART_INF;
+    } else {
+      v = (double)(float)s;
+    }
+    key[i] = v;
+  }
+  __syncthreads();
+  stable_order(key, n, order);
+}
+
+// ---- brute: exhaustive minimum-diameter subset (brute.py:47-68) -----------------------------
+// Thread t scans a contiguous range of lexicographic ranks; the first strict minimum wins,
+// so the block-wide winner is the smallest (diameter, thread) pair.
+__device__ __forceinline__ unsigned long long sat_add(unsigned long long a, unsigned long long b) {
+  const unsigned long long s = a + b;
+  return s < a ? ~0ull : s;
+}
+
+__global__ void __launch_bounds__(kK5Threads)
+k5_brute_select(const double* __restrict__ parts, int nparts, int n, int f, unsigned long long total,
+                int32_t* __restrict__ sel, int32_t* __restrict__ status) {
+  extern __shared__ double sm[];
+  double* dist = sm;                                                  // n*n
+  unsigned long long* binom = reinterpret_cast<unsigned long long*>(sm + n * n);   // (n+1)*(n+1)
+  __shared__ double best_diam[kK5Threads / 32];
+  __shared__ unsigned long long best_rank[kK5Threads / 32];
+  const int k = n - f;
+  const int W = n + 1;
+  load_distances(parts, nparts, n, false, 0., dist);
+  // Pascal triangle, row by row
+  for (int a = 0; a <= n; ++a) {
+    for (int b = threadIdx.x; b <= n; b += blockDim.x) {
+      unsigned long long v;
+      if (b == 0) v = 1;
+      else if (b > a) v = 0;
+      else v = sat_add(binom[(a - 1) * W + b - 1], binom[(a - 1) * W + b]);
+      binom[a * W + b] = v;
+    }
+    __syncthreads();
+  }
+  // This thread's rank range
+  const unsigned long long per = (total + blockDim.x - 1) / blockDim.x;
+  const unsigned long long lo = per * threadIdx.x;
+  const unsigned long long hi = (lo + per < total) ? lo + per : total;
+  double my_diam = CUDART_INF;
+  unsigned long long my_rank = ~0ull;
+  bool found = false;
+  if (lo < hi) {
+    int comb[kMaxN];
+    {  // unrank `lo`
+      unsigned long long r = lo;
+      int x = 0;
+      for (int pos = 0; pos < k; ++pos) {
+        while (true) {
+          const unsigned long long c = binom[(n - 1 - x) * W + (k - 1 - pos)];
+          if (c > r) break;
+          r -= c;
+          ++x;
+        }
+        comb[pos] = x++;
+      }
+    }
+    for (unsigned long long rank = lo; rank < hi; ++rank) {
+      double diam = 0.;
+      bool ok = true;
+      for (int a = 0; a < k - 1 && ok; ++a) {
+        const double* row = dist + comb[a] * n;
+        for (int b = a + 1; b < k; ++b) {
+          const double v = row[comb[b]];
+          if (!finite_d(v)) { ok = false; break; }
+          if (v > diam) diam = v;
+        }
+      }
+      if (ok && (!found || diam < my_diam)) { found = true; my_diam = diam; my_rank = rank; }
+      // next combination in lexicographic order
+      int pos = k - 1;
+      while (pos >= 0 && comb[pos] == n - k + pos) --pos;
+      if (pos < 0) break;
+      ++comb[pos];
+      for (int q = pos + 1; q < k; ++q) comb[q] = comb[q - 1] + 1;
+    }
+  }
+  // Block-wide minimum of (found ? diam : +inf-with-no-rank, rank)
+  double dm = found ? my_diam : CUDART_INF;
+  unsigned long long rk = found ? my_rank : ~0ull;
+  for (int h = 16; h >= 1; h >>= 1) {
+    const double od = __shfl_xor_sync(0xffffffffu, dm, h);
+    const unsigned long long orank = __shfl_xor_sync(0xffffffffu, rk, h);
+    if (orank != ~0ull && (rk == ~0ull || od < dm || (od == dm && orank < rk))) { dm = od; rk = orank; }
+  }
+  if ((threadIdx.x & 31) == 0) { best_diam[threadIdx.x >> 5] = dm; best_rank[threadIdx.x >> 5] = rk; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    dm = CUDART_INF; rk = ~0ull;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      const double od = best_diam[w];
+      const unsigned long long orank = best_rank[w];
+      if (orank != ~0ull && (rk == ~0ull || od < dm || (od == dm && orank < rk))) { dm = od; rk = orank; }
+    }
+    if (rk == ~0ull) {
+      if (status) *status = BZ_STATUS_NO_FINITE_SET;
+      for (int pos = 0; pos < k; ++pos) sel[pos] = pos;
+    } else {
+      if (status) *status = BZ_STATUS_OK;
+      unsigned long long r = rk;
+      int x = 0;
+      for (int pos = 0; pos < k; ++pos) {
+        while (true) {
+          const unsigned long long c = binom[(n - 1 - x) * W + (k - 1 - pos)];
+          if (c > r) break;
+          r -= c;
+          ++x;
+        }
+        sel[pos] = x++;
+      }
+    }
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------
+
+void launch_krum_select(const double* parts, int nparts, int n, int f, int32_t* order, cudaStream_t st) {
+  const size_t smem = (size_t)(2 * n * n + n) * sizeof(double);
+  static unsigned long long opted = 0;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(opted & bit)) {
+      cudaFuncSetAttribute(k5_score_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2 * kMaxN * kMaxN + kMaxN) * sizeof(double)));
+      opted |= bit;
+    }
+  }
+  k5_score_select<<<1, kK5Threads, smem, st>>>(parts, nparts, n, n - f - 1, order, nullptr, f, 0, 0);
+}
+
+void launch_bulyan_select(const double* parts, int nparts, int n, int f, int m, int32_t* order, int32_t* status, cudaStream_t st) {
+  const size_t smem = (size_t)(2 * n * n + n) * sizeof(double);
+  static unsigned long long opted = 0;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(opted & bit)) {
+      cudaFuncSetAttribute(k5_score_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2 * kMaxN * kMaxN + kMaxN) * sizeof(double)));
+      opted |= bit;
+    }
+  }
+  k5_score_select<<<1, kK5Threads, smem, st>>>(parts, nparts, n, m, order, status, f, m, 1);
+}
+
+int launch_brute_select(const double* parts, int nparts, int n, int f, int32_t* sel, int32_t* status, cudaStream_t st) {
+  // C(n, n-f) on the host, saturating
+  const int k = n - f;
+  unsigned long long total = 1;
+  for (int i = 1; i <= (k < n - k ? k : n - k); ++i) {
+    const unsigned long long num = (unsigned long long)(n - i + 1);
+    if (total > (~0ull) / num) { total = ~0ull; break; }
+    total = total * num / i;
+  }
+  if (total > (1ull << 31)) return -1;
+  const size_t smem = (size_t)n * n * sizeof(double) + (size_t)(n + 1) * (n + 1) * sizeof(unsigned long long);
+  static unsigned long long opted = 0;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(opted & bit)) {
+      cudaFuncSetAttribute(k5_brute_select, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(kMaxN * kMaxN * sizeof(double) + (kMaxN + 1) * (kMaxN + 1) * sizeof(unsigned long long)));
+      opted |= bit;
+    }
+  }
+  k5_brute_select<<<1, kK5Threads, smem, st>>>(parts, nparts, n, f, total, sel, status);
+  return 0;
+}
+
+void launch_rowdist_select(const double* parts, int nparts, int n, int sqrt_norm, int32_t* order, cudaStream_t st) {
+  k5_rowdist_select<<<1, 256, 0, st>>>(parts, nparts, n, sqrt_norm, order);
+}
+
+}  // namespace bz

@@ -1,0 +1,43 @@
+// launch.cuh — internal launch entry points shared between the kernel translation units
+// and api.cu.
+#pragma once
+
+#include "common.cuh"
+
+namespace bz {
+
+// Elements per thread in the aligned body of a K1 launch: 4 (LDG.128) while 4n values fit
+// the register file comfortably, else 2 (LDG.64).  The scalar variant (1) serves the
+// unaligned head/tail and rows whose alignments disagree.
+__host__ __device__ constexpr int body_vec(int n) { return n <= 28 ? 4 : 2; }
+
+// Epilogue of k1_sorted.
+enum SortedMode { kModeTrmean = 0, kModePhocas = 1, kModeMeamed = 2 };
+
+// K1 (k1_inst.cu, 8 parts).  Return false when n is outside the part's range.
+bool launch_median_part0(int n, int vec, const RowTable& rows, const Span& span, float* out, cudaStream_t st);
+bool launch_median_part1(int n, int vec, const RowTable& rows, const Span& span, float* out, cudaStream_t st);
+bool launch_median_part2(int n, int vec, const RowTable& rows, const Span& span, float* out, cudaStream_t st);
+bool launch_median_part3(int n, int vec, const RowTable& rows, const Span& span, float* out, cudaStream_t st);
+bool launch_sorted_part4(int n, int vec, const RowTable& rows, const Span& span, int mode, int f, float* out, cudaStream_t st);
+bool launch_sorted_part5(int n, int vec, const RowTable& rows, const Span& span, int mode, int f, float* out, cudaStream_t st);
+bool launch_sorted_part6(int n, int vec, const RowTable& rows, const Span& span, int mode, int f, float* out, cudaStream_t st);
+bool launch_sorted_part7(int n, int vec, const RowTable& rows, const Span& span, int mode, int f, float* out, cudaStream_t st);
+
+// K3 (k3_average.cu): ordered-subset average.
+void launch_average(int vec, const RowTable& rows, const Span& span, const int32_t* sel, int count,
+                    int zero_init, float divisor, const int32_t* status, float* out, cudaStream_t st);
+
+// Opt a kernel into > 48 KB of dynamic shared memory once per device.
+template <class K>
+inline void opt_in_smem(K kernel, size_t bytes, unsigned long long& done_mask) {
+  if (bytes <= 48 * 1024) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done_mask & bit) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  done_mask |= bit;
+}
+
+}  // namespace bz

@@ -1,0 +1,317 @@
+# coding: utf-8
+"""Host side of the CUDA path: turns a list of n flat fp32 tensors into ONE call of the C ABI.
+
+PyTorch is plumbing here (device memory, the current stream, the caching allocator); every
+numeric operation happens in `libbyzagg.so`.  The gradients are never stacked: the library
+receives the n row pointers (`tensor.data_ptr()`) and reads the rows where they live.
+
+CPU tensors (`--device-gar cpu` in the reference's attack.py:66-69) are staged to the
+current CUDA device — each distinct tensor object once, so the f aliased Byzantine entries
+(attacks/identical.py:86) cost one copy — and the result is copied back: that is the
+"host buffers" end-to-end path `bench.py` times.  Without a CUDA device or without the
+compiled library every entry point raises; there is no CPU fallback.
+"""
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+__all__ = ["average", "median", "trmean", "phocas", "meamed", "krum", "bulyan", "brute", "aksel", "cge",
+           "pairdist_partial", "rowdist_partial", "krum_select", "bulyan_select", "brute_select",
+           "rowdist_select", "average_selected", "bulyan_reduce", "config", "DataError"]
+
+class DataError(Exception):
+  """ Placeholder base; the concrete errors raised mirror the reference (AssertionError, TypeError). """
+
+class _Config:
+  """ strict_status: after brute / bulyan, read the device status word (one 4-byte D2H copy,
+  i.e. a stream sync) and raise where the reference raises (brute.py:67, bulyan.py:70).
+  When False the call stays asynchronous and a failed rule yields an all-NaN vector. """
+  strict_status = True
+config = _Config()
+
+# ---------------------------------------------------------------------------- #
+# Argument plumbing
+
+class _Prepared:
+  __slots__ = ("rows", "n", "d", "device", "ptrs", "stream", "to_cpu", "keep")
+
+_workspaces = {}
+_staging = {}
+
+def _workspace(device, stream):
+  key = (device.index, stream)
+  ws = _workspaces.get(key)
+  if ws is None:
+    nbytes = int(_lib.lib().bz_workspace_bytes(_lib.MAX_N))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    _workspaces[key] = ws
+  return ws
+
+def _validate(gradients):
+  if not isinstance(gradients, (list, tuple)) or len(gradients) < 1:
+    raise ValueError(f"expected a non-empty list of gradients, got {type(gradients).__name__} of length {len(gradients) if hasattr(gradients, '__len__') else '?'}")
+  first = gradients[0]
+  if not isinstance(first, torch.Tensor):
+    raise TypeError(f"gradients must be torch tensors, got {type(first).__name__}")
+  if len(gradients) > _lib.MAX_N:
+    raise ValueError(f"{len(gradients)} gradients exceed the supported maximum of {_lib.MAX_N}")
+  for grad in gradients:
+    if grad.dtype != torch.float32:
+      raise TypeError(f"gradients must be float32 (attack.py:461 fixes the dtype), got {grad.dtype}")
+    if grad.dim() != 1 or grad.shape != first.shape or grad.device != first.device:
+      raise ValueError("gradients must be 1-D tensors of one shape on one device")
+  return first
+
+def _prepare(gradients):
+  first = _validate(gradients)
+  if not torch.cuda.is_available():
+    raise _lib.LibraryError("no CUDA device available: byzantinemomentum_b200 runs on B200 GPUs only (no CPU fallback)")
+  _lib.lib()
+  prep = _Prepared()
+  n, d = len(gradients), first.shape[0]
+  keep = None
+  if first.device.type == "cuda":
+    device = first.device
+    rows = [g if g.is_contiguous() else g.contiguous() for g in gradients]
+    prep.to_cpu = False
+  elif first.device.type == "cpu":
+    # Stage every distinct tensor object once into a cached [k, d] device buffer
+    device = torch.device("cuda", torch.cuda.current_device())
+    uniq = {}
+    for g in gradients:
+      uniq.setdefault(id(g), g)
+    key = (device.index, len(uniq), d)
+    buf = _staging.get(key)
+    if buf is None:
+      _staging.clear()
+      buf = torch.empty((len(uniq), d), dtype=torch.float32, device=device)
+      _staging[key] = buf
+    slot = {}
+    for k, (ident, g) in enumerate(uniq.items()):
+      buf[k].copy_(g, non_blocking=True)
+      slot[ident] = buf[k]
+    rows = [slot[id(g)] for g in gradients]
+    keep = buf
+    prep.to_cpu = True
+  else:
+    raise ValueError(f"unsupported device {first.device}")
+  prep.rows, prep.n, prep.d, prep.device, prep.keep = rows, n, d, device, keep
+  prep.ptrs = (ctypes.c_void_p * n)(*[g.data_ptr() for g in rows])
+  prep.stream = torch.cuda.current_stream(device).cuda_stream
+  return prep
+
+class _on:
+  """ Make `device` current for the launches (cheap when it already is). """
+  __slots__ = ("device", "prev")
+  def __init__(self, device):
+    self.device = device
+    self.prev = None
+  def __enter__(self):
+    cur = torch.cuda.current_device()
+    if cur != self.device.index:
+      self.prev = cur
+      torch.cuda.set_device(self.device)
+  def __exit__(self, *exc):
+    if self.prev is not None:
+      torch.cuda.set_device(self.prev)
+
+def _finish(prep, out):
+  return out.cpu() if prep.to_cpu else out
+
+def _raise_status(code):
+  if code == _lib.STATUS_NO_FINITE_SET:
+    raise AssertionError(_lib.STATUS_MESSAGES[code])        # brute.py:67
+  if code == _lib.STATUS_DEGENERATE:
+    raise TypeError(_lib.STATUS_MESSAGES[code])             # bulyan.py:70 (`gradients[None]`)
+
+# ---------------------------------------------------------------------------- #
+# Coordinate-wise rules
+
+def _coordinate(name, gradients, f=None):
+  prep = _prepare(gradients)
+  out = torch.empty(prep.d, dtype=torch.float32, device=prep.device)
+  fn = getattr(_lib.lib(), "bz_" + name)
+  with _on(prep.device):
+    if f is None:
+      code = fn(prep.ptrs, prep.n, prep.d, out.data_ptr(), prep.stream)
+    else:
+      code = fn(prep.ptrs, prep.n, int(f), prep.d, out.data_ptr(), prep.stream)
+  _lib.check(code, "bz_" + name)
+  return _finish(prep, out)
+
+def average(gradients):
+  return _coordinate("average", gradients)
+
+def median(gradients):
+  return _coordinate("median", gradients)
+
+def trmean(gradients, f):
+  return _coordinate("trmean", gradients, f)
+
+def phocas(gradients, f):
+  return _coordinate("phocas", gradients, f)
+
+def meamed(gradients, f):
+  return _coordinate("meamed", gradients, f)
+
+# ---------------------------------------------------------------------------- #
+# Distance-based rules (single device).  Each returns (out, selection) where `selection` is a
+# DEVICE int32 tensor (all n indices by increasing score/distance; brute: the n-f subset).
+
+def _aux(prep):
+  ws = _workspace(prep.device, prep.stream)
+  meta = torch.empty(prep.n + 1, dtype=torch.int32, device=prep.device)   # order[n] + status
+  return ws, meta
+
+def krum(gradients, f, m):
+  prep = _prepare(gradients)
+  out = torch.empty(prep.d, dtype=torch.float32, device=prep.device)
+  ws, meta = _aux(prep)
+  with _on(prep.device):
+    code = _lib.lib().bz_krum(prep.ptrs, prep.n, int(f), int(m), prep.d, out.data_ptr(), meta.data_ptr(),
+                              ws.data_ptr(), ws.numel(), prep.stream)
+  _lib.check(code, "bz_krum")
+  return _finish(prep, out), meta[:prep.n]
+
+def bulyan(gradients, f, m):
+  prep = _prepare(gradients)
+  out = torch.empty(prep.d, dtype=torch.float32, device=prep.device)
+  ws, meta = _aux(prep)
+  status = meta[prep.n:]
+  with _on(prep.device):
+    code = _lib.lib().bz_bulyan(prep.ptrs, prep.n, int(f), int(m), prep.d, out.data_ptr(), meta.data_ptr(),
+                                status.data_ptr(), ws.data_ptr(), ws.numel(), prep.stream)
+  _lib.check(code, "bz_bulyan")
+  if config.strict_status:
+    _raise_status(int(status.item()))
+  return _finish(prep, out), meta[:prep.n]
+
+def brute(gradients, f):
+  prep = _prepare(gradients)
+  out = torch.empty(prep.d, dtype=torch.float32, device=prep.device)
+  ws, meta = _aux(prep)
+  status = meta[prep.n:]
+  with _on(prep.device):
+    code = _lib.lib().bz_brute(prep.ptrs, prep.n, int(f), prep.d, out.data_ptr(), meta.data_ptr(),
+                               status.data_ptr(), ws.data_ptr(), ws.numel(), prep.stream)
+  _lib.check(code, "bz_brute")
+  if config.strict_status:
+    _raise_status(int(status.item()))
+  return _finish(prep, out), meta[:prep.n - int(f)]
+
+def aksel(gradients, f, mode="mid"):
+  if mode not in _lib.AKSEL_MODES:
+    raise NotImplementedError(mode)      # aksel.py:47-48
+  prep = _prepare(gradients)
+  out = torch.empty(prep.d, dtype=torch.float32, device=prep.device)
+  ws, meta = _aux(prep)
+  with _on(prep.device):
+    code = _lib.lib().bz_aksel(prep.ptrs, prep.n, int(f), _lib.AKSEL_MODES[mode], prep.d, out.data_ptr(),
+                               meta.data_ptr(), ws.data_ptr(), ws.numel(), prep.stream)
+  _lib.check(code, "bz_aksel")
+  return _finish(prep, out), meta[:prep.n]
+
+def cge(gradients, f):
+  prep = _prepare(gradients)
+  out = torch.empty(prep.d, dtype=torch.float32, device=prep.device)
+  ws, meta = _aux(prep)
+  with _on(prep.device):
+    code = _lib.lib().bz_cge(prep.ptrs, prep.n, int(f), prep.d, out.data_ptr(), meta.data_ptr(),
+                             ws.data_ptr(), ws.numel(), prep.stream)
+  _lib.check(code, "bz_cge")
+  return _finish(prep, out), meta[:prep.n]
+
+# ---------------------------------------------------------------------------- #
+# Phases of the d-sharded multi-GPU path (device tensors only)
+
+def _prepare_device(gradients):
+  prep = _prepare(gradients)
+  if prep.to_cpu:
+    raise ValueError("the sharded phases take CUDA tensors")
+  return prep
+
+def pairdist_partial(gradients):
+  """ [n, n] fp64: this shard's share of the squared pairwise distances (entries i < j). """
+  prep = _prepare_device(gradients)
+  part = torch.empty((prep.n, prep.n), dtype=torch.float64, device=prep.device)
+  ws = _workspace(prep.device, prep.stream)
+  with _on(prep.device):
+    code = _lib.lib().bz_pairdist_partial(prep.ptrs, prep.n, prep.d, part.data_ptr(), ws.data_ptr(), ws.numel(), prep.stream)
+  _lib.check(code, "bz_pairdist_partial")
+  return part
+
+def rowdist_partial(gradients, center=None):
+  """ [n] fp64: this shard's share of the squared distance of every row to `center` (None: origin). """
+  prep = _prepare_device(gradients)
+  part = torch.empty(prep.n, dtype=torch.float64, device=prep.device)
+  ws = _workspace(prep.device, prep.stream)
+  cptr = None
+  if center is not None:
+    if center.dtype != torch.float32 or center.shape != (prep.d,) or center.device != prep.device or not center.is_contiguous():
+      raise ValueError("center must be a contiguous float32 vector like the rows")
+    cptr = center.data_ptr()
+  with _on(prep.device):
+    code = _lib.lib().bz_rowdist_partial(prep.ptrs, prep.n, cptr, prep.d, part.data_ptr(), ws.data_ptr(), ws.numel(), prep.stream)
+  _lib.check(code, "bz_rowdist_partial")
+  return part
+
+def _select_common(parts, n):
+  if parts.dtype != torch.float64 or not parts.is_contiguous() or parts.device.type != "cuda":
+    raise ValueError("parts must be a contiguous float64 CUDA tensor")
+  nparts = parts.shape[0]
+  meta = torch.empty(n + 1, dtype=torch.int32, device=parts.device)
+  stream = torch.cuda.current_stream(parts.device).cuda_stream
+  return nparts, meta, stream
+
+def krum_select(parts, n, f):
+  """ parts: [R, n, n] gathered partial blocks -> order (device int32[n]). """
+  nparts, meta, stream = _select_common(parts, n)
+  with _on(parts.device):
+    code = _lib.lib().bz_krum_select(parts.data_ptr(), nparts, n, int(f), meta.data_ptr(), stream)
+  _lib.check(code, "bz_krum_select")
+  return meta[:n]
+
+def bulyan_select(parts, n, f, m):
+  nparts, meta, stream = _select_common(parts, n)
+  with _on(parts.device):
+    code = _lib.lib().bz_bulyan_select(parts.data_ptr(), nparts, n, int(f), int(m), meta.data_ptr(), meta[n:].data_ptr(), stream)
+  _lib.check(code, "bz_bulyan_select")
+  return meta[:n], meta[n:]
+
+def brute_select(parts, n, f):
+  nparts, meta, stream = _select_common(parts, n)
+  with _on(parts.device):
+    code = _lib.lib().bz_brute_select(parts.data_ptr(), nparts, n, int(f), meta.data_ptr(), meta[n:].data_ptr(), stream)
+  _lib.check(code, "bz_brute_select")
+  return meta[:n - int(f)], meta[n:]
+
+def rowdist_select(parts, n, sqrt_norm):
+  nparts, meta, stream = _select_common(parts, n)
+  with _on(parts.device):
+    code = _lib.lib().bz_rowdist_select(parts.data_ptr(), nparts, n, 1 if sqrt_norm else 0, meta.data_ptr(), stream)
+  _lib.check(code, "bz_rowdist_select")
+  return meta[:n]
+
+def average_selected(gradients, selection, count, zero_init=True, divisor=None, status=None):
+  """ Ordered-subset average of the local shard; `selection` is a device int32 tensor or None. """
+  prep = _prepare_device(gradients)
+  out = torch.empty(prep.d, dtype=torch.float32, device=prep.device)
+  sel_ptr = None if selection is None else selection.data_ptr()
+  st_ptr = None if status is None else status.data_ptr()
+  with _on(prep.device):
+    code = _lib.lib().bz_average_selected(prep.ptrs, prep.n, sel_ptr, int(count), 1 if zero_init else 0,
+                                          float(count if divisor is None else divisor), st_ptr, prep.d, out.data_ptr(), prep.stream)
+  _lib.check(code, "bz_average_selected")
+  return out
+
+def bulyan_reduce(gradients, f, m, order, status=None):
+  prep = _prepare_device(gradients)
+  out = torch.empty(prep.d, dtype=torch.float32, device=prep.device)
+  st_ptr = None if status is None else status.data_ptr()
+  with _on(prep.device):
+    code = _lib.lib().bz_bulyan_reduce(prep.ptrs, prep.n, int(f), int(m), order.data_ptr(), st_ptr, prep.d, out.data_ptr(), prep.stream)
+  _lib.check(code, "bz_bulyan_reduce")
+  return out

@@ -1,0 +1,140 @@
+/* byzagg.h — C ABI of libbyzagg (B200 / sm_100a Byzantine-robust gradient aggregation).
+ *
+ * Drop-in boundary for the aggregation rules (GARs) of LPD-EPFL/ByzantineMomentum.
+ * Each entry point replaces one Python/ATen implementation in the reference (citations
+ * are relative to the reference root) and is what the reference's optional `native`
+ * hook (`native.<gar>.aggregate`, aggregators/median.py:41-49, krum.py:82-96,
+ * bulyan.py:86-100, brute.py:82-91) or an `aggregators.register(...)` plugin binds.
+ *
+ * Conventions
+ *   - `rows` is a HOST array of n DEVICE pointers; row i is a contiguous fp32 vector of
+ *     d elements (the list `gradients` of aggregators/__init__.py:17-21).  Rows may alias
+ *     (the f Byzantine entries are one tensor repeated, attacks/identical.py:86) and only
+ *     need 4-byte alignment (d-shard views); they are never written.
+ *   - `out` is a DEVICE fp32 vector of d elements owned by the caller; it must not overlap
+ *     any row (aggregators/__init__.py:21).
+ *   - `ws` is a caller-owned DEVICE scratch buffer of at least bz_workspace_bytes(n) bytes,
+ *     8-byte aligned; the library allocates no device memory.  One workspace per stream.
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).  All
+ *     work is enqueued on it; no entry point synchronises the host.
+ *   - `sel` / `order` outputs are DEVICE int32 arrays (may be NULL where stated) so that a
+ *     following kernel can consume them without a host round trip.
+ *   - `status` is a DEVICE int32 (may be NULL): set to 0 on success or to a BZ_STATUS_* code
+ *     when the DATA makes the rule undefined (the reference raises there); `out` is then
+ *     filled with NaN.
+ *   - Return value: 0 on success, a negative BZ_E* code otherwise; bz_last_error() returns
+ *     a thread-local message for the last failure.
+ *   - 1 <= n <= bz_max_n() (= 64), d >= 0 (d = 0 is a no-op).
+ *   - Parameter validity (f, m ranges) is the caller's job, exactly like the reference's
+ *     `check()` functions; the library only rejects what it cannot execute.
+ */
+#ifndef BYZAGG_H
+#define BYZAGG_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define BZ_API __attribute__((visibility("default")))
+#else
+#define BZ_API
+#endif
+
+#define BZ_MAX_N 64
+
+#define BZ_OK            0
+#define BZ_EINVAL       -1   /* bad argument (null pointer, n/f/m out of executable range) */
+#define BZ_EUNSUPPORTED -2   /* valid for the reference, not executable here (n > BZ_MAX_N, too many subsets) */
+#define BZ_ECUDA        -3   /* CUDA runtime error; message in bz_last_error() */
+#define BZ_EWORKSPACE   -4   /* workspace too small or misaligned */
+
+#define BZ_STATUS_OK            0
+#define BZ_STATUS_NO_FINITE_SET 1  /* brute: every subset holds a non-finite distance (brute.py:67 assert) */
+#define BZ_STATUS_DEGENERATE    2  /* bulyan: too few finite scores (bulyan.py:70 fails on gradients[None]) */
+
+/* Aksel modes (aggregators/aksel.py:43-48) */
+#define BZ_AKSEL_MID 0   /* c = (n + 1) / 2 */
+#define BZ_AKSEL_NF  1   /* c = n - f       */
+
+BZ_API int         bz_version(void);
+BZ_API int         bz_max_n(void);
+BZ_API const char* bz_last_error(void);
+/* Bytes of device scratch the distance-based rules need for n rows (multiple of 256). */
+BZ_API size_t      bz_workspace_bytes(int n);
+
+/* ---- Coordinate-wise rules (shard along d with no collective) ---------------------- */
+
+/* aggregators/average.py:21-29 — ((0 + g0) + g1) + ... then / n, fp32, IEEE division. */
+BZ_API int bz_average(const float* const* rows, int n, int64_t d, float* out, void* stream);
+/* aggregators/median.py:31-39 — lower median per coordinate, NaN-propagating. */
+BZ_API int bz_median(const float* const* rows, int n, int64_t d, float* out, void* stream);
+/* aggregators/trmean.py:24-33,69-79 — mean of ranks f..n-f-1 (NaN sorts last), ATen order. */
+BZ_API int bz_trmean(const float* const* rows, int n, int f, int64_t d, float* out, void* stream);
+/* aggregators/trmean.py:35-50,81-94 — mean of the n-f values closest to the trimmed mean. */
+BZ_API int bz_phocas(const float* const* rows, int n, int f, int64_t d, float* out, void* stream);
+/* aggregators/trmean.py:35-50,96-109 — mean of the n-f values closest to the median. */
+BZ_API int bz_meamed(const float* const* rows, int n, int f, int64_t d, float* out, void* stream);
+
+/* ---- Distance-based rules, whole vector on this device ------------------------------ */
+
+/* aggregators/krum.py:31-80 — Multi-Krum.  order (n entries, may be NULL) receives all row
+ * indices by increasing score (stable); the first m are the averaged selection. */
+BZ_API int bz_krum(const float* const* rows, int n, int f, int m, int64_t d, float* out,
+            int32_t* order, void* ws, size_t ws_bytes, void* stream);
+/* aggregators/bulyan.py:31-84 — Bulyan over Multi-Krum (scores never updated, :74-76). */
+BZ_API int bz_bulyan(const float* const* rows, int n, int f, int m, int64_t d, float* out,
+              int32_t* order, int32_t* status, void* ws, size_t ws_bytes, void* stream);
+/* aggregators/brute.py:32-80 — minimum-diameter subset of size n-f, then its average.
+ * sel (n-f entries, may be NULL) receives the subset, ascending. */
+BZ_API int bz_brute(const float* const* rows, int n, int f, int64_t d, float* out,
+             int32_t* sel, int32_t* status, void* ws, size_t ws_bytes, void* stream);
+/* aggregators/aksel.py:24-64 — average of the c rows closest to the median (squared L2). */
+BZ_API int bz_aksel(const float* const* rows, int n, int f, int mode, int64_t d, float* out,
+             int32_t* order, void* ws, size_t ws_bytes, void* stream);
+/* aggregators/cge.py:28-57 — average of the n-f smallest-norm rows (clone + add_ + div_). */
+BZ_API int bz_cge(const float* const* rows, int n, int f, int64_t d, float* out,
+           int32_t* order, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- Phases for the d-sharded multi-GPU path ------------------------
+ * Each rank runs phase A on its shard, the R partial blocks are all-gathered (one small
+ * collective, done by the host side with torch.distributed/NCCL), phase B sums them in
+ * rank order — bitwise identical on every rank — and derives the selection, phase C
+ * reduces the local shard. */
+
+/* A: partial squared pairwise distances of the shard: part[i*n+j] (i<j) = sum_k (x_i-x_j)^2,
+ *    fp64, other entries 0.  part: device double[n*n]. */
+BZ_API int bz_pairdist_partial(const float* const* rows, int n, int64_t d, double* part,
+                        void* ws, size_t ws_bytes, void* stream);
+/* A': partial squared distance of every row to `center` (device fp32[d], or NULL for the
+ *    origin: squared norms).  part: device double[n]. */
+BZ_API int bz_rowdist_partial(const float* const* rows, int n, const float* center, int64_t d,
+                       double* part, void* ws, size_t ws_bytes, void* stream);
+/* B: selections from `nparts` gathered blocks (parts: device double[nparts][n*n] or [nparts][n]). */
+BZ_API int bz_krum_select(const double* parts, int nparts, int n, int f, int32_t* order, void* stream);
+BZ_API int bz_bulyan_select(const double* parts, int nparts, int n, int f, int m, int32_t* order,
+                     int32_t* status, void* stream);
+BZ_API int bz_brute_select(const double* parts, int nparts, int n, int f, int32_t* sel,
+                    int32_t* status, void* stream);
+/* sqrt_norm != 0: keys are fl32(sqrt(sum)) with non-finite -> +inf (cge.py:36-37);
+ * sqrt_norm == 0: keys are fl32(sum) (aksel.py:41).  Stable ascending order of the n keys. */
+BZ_API int bz_rowdist_select(const double* parts, int nparts, int n, int sqrt_norm, int32_t* order,
+                      void* stream);
+/* C: out = (((z + g[sel[0]]) + g[sel[1]]) + ...) / divisor over the local shard; z = 0.0f when
+ *    zero_init (Python sum(), krum.py:80) else the first row itself (cge.py:53).  sel: device
+ *    int32[count], or NULL for 0..count-1; divisor is rounded to fp32 (normally = count).
+ *    status (device, may be NULL): non-zero -> NaN fill. */
+BZ_API int bz_average_selected(const float* const* rows, int n, const int32_t* sel, int count,
+                        int zero_init, double divisor, const int32_t* status, int64_t d,
+                        float* out, void* stream);
+/* C (bulyan): stage 1 means over `order` + coordinate-wise averaged median (bulyan.py:64-84). */
+BZ_API int bz_bulyan_reduce(const float* const* rows, int n, int f, int m, const int32_t* order,
+                     const int32_t* status, int64_t d, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BYZAGG_H */
