@@ -1,0 +1,356 @@
+#!/usr/bin/env python3
+# coding: utf-8
+"""bench.py — throughput of the aggregation hot path on synthetic [n, d] gradients.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--gar trmean --n 25 --f 10 --d 1310922] [--no-sweep]
+
+A "step" is ONE aggregation call over one stack of n worker gradients (fp32, length d per
+GPU).  Default workload = BASELINE.json configs[1]: trimmed mean, n=25, f=10, d=1,310,922
+(CIFAR-10 `empire-cnn`), the configuration the headline metric is quoted on.
+N > 1 (launched by torchrun, one rank per GPU, NCCL): the d axis is sharded, every rank
+aggregates its own [n, d] shard; coordinate-wise rules need no collective, distance-based
+rules all-gather their n x n partial-distance blocks (byzantinemomentum_b200.sharded).
+Per-GPU work is fixed as N grows -> "scaling": "weak"; `value` = N*d / step time.
+
+One JSON line is printed by rank 0 (see the driver contract in the task statement):
+  value       params/s with inputs resident in HBM, device-timed (CUDA events, max over ranks)
+  roofline    dominant kernel: algorithmic bytes / average per-launch duration vs the measured
+              HBM peak of MEASURED_PEAKS.json
+  e2e         the same metric through the reference-facing call `gars[gar](gradients=<host
+              tensors>, f=f)`: pinned host rows -> H2D -> kernel -> D2H of the result, per step
+  cpu_baseline  the reference's ATen operator sequence (oracle/refcost.py) on the host cores
+  sweep       (N=1) kernel time / GB/s / roofline fraction of the other rules and sizes
+`--impl reference` times the CPU operator sequence alone, on the same workload.
+"""
+
+import argparse
+import json
+import math
+import os
+import pathlib
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+L2_BYTES = 126 * 1024 * 1024
+FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md, used only without MEASURED_PEAKS.json
+
+# kernels of libbyzagg launched per aggregation call (single device)
+LAUNCHES = dict(average=1, median=1, trmean=1, phocas=1, meamed=1, krum=3, bulyan=3, brute=3, aksel=4, cge=3)
+
+def algorithmic_bytes(gar, n, f, d, m=None):
+  """ bytes one call must move, per GAR (no credit for aliases or L2 hits). """
+  if gar in ("average", "median", "trmean", "phocas", "meamed"):
+    units = n + 1
+  elif gar in ("krum", "bulyan"):
+    units = n + (m if m is not None else n - f - 2) + 1
+  elif gar in ("brute", "cge"):
+    units = n + (n - f) + 1
+  elif gar == "aksel":
+    units = n + (n + 1) // 2 + 1
+  else:
+    raise KeyError(gar)
+  return units * d * 4
+
+def default_f(gar, n, f):
+  if gar in ("bulyan",):
+    return min(f, (n - 3) // 4)
+  if gar in ("krum",):
+    return min(f, (n - 3) // 2)
+  return f
+
+# ---------------------------------------------------------------------------- #
+# Clock sampling (NVML), during the timed regions
+
+class ClockSampler:
+  REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+             0x80: "hw_power_brake", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+  def __init__(self, index):
+    self.samples, self.reasons, self.max_mhz = [], set(), None
+    self._stop = threading.Event()
+    self._thread = None
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self.nv = pynvml
+      self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+      self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+    except Exception:
+      self.nv = None
+  def _loop(self):
+    nv = self.nv
+    while not self._stop.is_set():
+      try:
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+          else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        for bit, name in self.REASONS.items():
+          if mask & bit:
+            self.reasons.add(name)
+      except Exception:
+        pass
+      self._stop.wait(0.005)
+  def __enter__(self):
+    if self.nv is not None:
+      self._thread = threading.Thread(target=self._loop, daemon=True)
+      self._thread.start()
+    return self
+  def __exit__(self, *exc):
+    self._stop.set()
+    if self._thread is not None:
+      self._thread.join()
+  def summary(self):
+    if not self.samples:
+      return dict(sm_mhz=None, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=0)
+    s = sorted(self.samples)
+    return dict(sm_mhz=s[len(s) // 2], sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(s))
+
+# ---------------------------------------------------------------------------- #
+
+def make_rows(torch, n, d, device, seed, sets):
+  """ `sets` independent stacks of n rows ~ N(0, 1) (distribution A of SURVEY.md §8(d)). """
+  gen = torch.Generator(device=device).manual_seed(seed)
+  return [[torch.randn(d, device=device, generator=gen) for _ in range(n)] for _ in range(sets)]
+
+def call_device(bz, sharded, gar, rows, f, world):
+  """ One aggregation of device-resident rows (the step of the timed region). """
+  if world > 1:
+    return sharded.aggregate(gar, rows, f=f)
+  return bz.gars[gar].unchecked(gradients=rows, f=f)
+
+def time_steps(torch, fn, steps):
+  """ Per-step CUDA event pairs on the current stream; returns (total_ms, per_step_ms list). """
+  ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+  for k in range(steps):
+    ev[k][0].record()
+    fn(k)
+    ev[k][1].record()
+  torch.cuda.synchronize()
+  total = ev[0][0].elapsed_time(ev[-1][1])
+  return total, [a.elapsed_time(b) for a, b in ev]
+
+def peak_hbm():
+  path = ROOT / "MEASURED_PEAKS.json"
+  try:
+    return float(json.loads(path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+  except Exception:
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+def recorded_traffic(gar, n, f, d):
+  """ dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture. """
+  try:
+    table = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+    return table.get(f"{gar}:n{n}:f{f}:d{d}")
+  except Exception:
+    return None
+
+def cpu_reference(torch, gar, n, f, d, seed, budget_s, repeats):
+  """ oracle/refcost.py on the host cores, bounded: shrinks d so that `repeats` calls fit `budget_s`. """
+  from oracle import refcost
+  threads = os.cpu_count() or 1
+  torch.set_num_threads(threads)
+  gen = torch.Generator().manual_seed(seed)
+  probe_d = min(d, 65536)
+  rows = [torch.randn(probe_d, generator=gen) for _ in range(n)]
+  t0 = time.perf_counter()
+  refcost.run(gar, rows, f=f)
+  per_elem = (time.perf_counter() - t0) / probe_d
+  sample_d = int(min(d, max(4096, budget_s / max(repeats, 1) / max(per_elem, 1e-12))))
+  rows = [torch.randn(sample_d, generator=gen) for _ in range(n)]
+  refcost.run(gar, rows, f=f)  # warm
+  times = []
+  for _ in range(repeats):
+    t0 = time.perf_counter()
+    refcost.run(gar, rows, f=f)
+    times.append(time.perf_counter() - t0)
+  return dict(times=times, sample_d=sample_d, threads=torch.get_num_threads())
+
+# ---------------------------------------------------------------------------- #
+
+def run_reference(args):
+  import torch
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  f = default_f(args.gar, args.n, args.f)
+  res = cpu_reference(torch, args.gar, args.n, f, args.d, 4321, budget_s=120.0, repeats=args.steps + args.warmup)
+  times = res["times"][args.warmup:] or res["times"]
+  ms = 1e3 * sum(times) / len(times)
+  value = res["sample_d"] / (ms * 1e-3)
+  sample = f"{args.gar} n={args.n} f={f} on d={res['sample_d']} of {args.d} columns per step, {len(times)} timed steps"
+  line = dict(impl="reference", metric="aggregated-params/sec", value=value, unit="params/s", n_gpus=args.gpus, steps=len(times),
+              warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+              config=dict(workload=f"{args.gar} GAR, n={args.n} f={f}, d={args.d} (BASELINE.json configs[1] shape)", gar=args.gar, n=args.n,
+                          f=f, d=args.d, path="oracle/refcost.py: the reference's ATen operator sequence on CPU tensors"),
+              cpu_baseline=dict(value=value, unit="params/s", cores=res["threads"], kind="port", sample=sample),
+              e2e=dict(value=value, unit="params/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+  print(json.dumps(line), flush=True)
+
+def run_b200(args):
+  import torch
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py needs a CUDA device (the CUDA path has no CPU fallback); use --impl reference for the CPU arm")
+  torch.cuda.set_device(local)
+  device = torch.device("cuda", local)
+  dist = None
+  if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=device)
+  import byzantinemomentum_b200 as bz
+  from byzantinemomentum_b200 import sharded
+  bz._lib.lib()
+  gar, n, d = args.gar, args.n, args.d
+  f = default_f(gar, n, args.f)
+  set_bytes = n * d * 4
+  sets = max(1, min(8, math.ceil(3 * L2_BYTES / set_bytes)))
+  inputs = make_rows(torch, n, d, device, 1234 + rank, sets)
+  def barrier():
+    if dist is not None:
+      dist.barrier()
+    torch.cuda.synchronize()
+  step = lambda k: call_device(bz, sharded, gar, inputs[k % sets], f, world)
+  for k in range(max(args.warmup, 3)):
+    step(k)
+  barrier()
+  with ClockSampler(local) as clocks:
+    total_ms, per_step = time_steps(torch, step, args.steps)
+    barrier()
+    # keep the sampler alive a little when the region is very short
+    if total_ms < 50:
+      t_end = time.perf_counter() + 0.05
+      k = 0
+      while time.perf_counter() < t_end:
+        step(k); k += 1
+      torch.cuda.synchronize()
+  if dist is not None:
+    t = torch.tensor([total_ms], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+  ms_per_step = total_ms / args.steps
+  value = world * d / (ms_per_step * 1e-3)
+  kernel_ms = sum(per_step) / len(per_step)
+  peak, peak_src = peak_hbm()
+  alg = algorithmic_bytes(gar, n, f, d)
+  achieved = alg / (kernel_ms * 1e-3) / 1e9
+  roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=recorded_traffic(gar, n, f, d),
+                  kernel=("k1_sorted" if gar in ("trmean", "phocas", "meamed") else "k1_median" if gar == "median" else "k3_average" if gar == "average" else "k2_pairdist"),
+                  algorithmic_bytes=alg, read_only_frac=(n * d * 4) / (kernel_ms * 1e-3) / 1e9 / peak, kernel_ms=kernel_ms, peak_source=peak_src)
+
+  # ---- end to end through the reference-facing call with HOST buffers ---------------------------
+  e2e_steps = max(3, min(args.steps, 20))
+  host_sets = 2
+  host = [[torch.randn(d, generator=torch.Generator().manual_seed(99 + 7 * s + r)).pin_memory() for r in range(n)] for s in range(host_sets)]
+  def e2e_step(k):
+    out = bz.gars[gar].unchecked(gradients=host[k % host_sets], f=f)
+    assert out.device.type == "cpu"
+    return out
+  for k in range(2):
+    e2e_step(k)
+  barrier()
+  e2e_total, _ = time_steps(torch, e2e_step, e2e_steps)
+  if dist is not None:
+    t = torch.tensor([e2e_total], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_total = float(t.item())
+  e2e_ms = e2e_total / e2e_steps
+  e2e = dict(value=world * d / (e2e_ms * 1e-3), unit="params/s", h2d_bytes_per_step=n * d * 4, d2h_bytes_per_step=d * 4,
+             ms_per_step=e2e_ms, steps=e2e_steps, call=f"byzantinemomentum_b200.gars[{gar!r}].unchecked(gradients=<{n} pinned host tensors>, f={f})")
+  del host
+
+  line = dict(metric="aggregated-params/sec", value=value, unit="params/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+              ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+              config=dict(workload=f"{gar} GAR, n={n} f={f}, d={d} per GPU (BASELINE.json configs[1]: CIFAR-10 empire-cnn shape)",
+                          gar=gar, n=n, f=f, d=d, parallelism=f"d-sharded x{world}" if world > 1 else "single GPU",
+                          l2="inputs rotate over %d independent [n, d] stacks (%.0f MB > L2)" % (sets, sets * set_bytes / 1e6)),
+              roofline=roofline, e2e=e2e, gpu_launches=args.steps * LAUNCHES[gar], clocks=clocks.summary())
+  if rank == 0 and world == 1:
+    # ---- CPU baseline: the reference's operator sequence on the host cores (bounded sample) --------
+    res = cpu_reference(torch, gar, n, f, d, 4321, budget_s=20.0, repeats=3)
+    best = min(res["times"])
+    line["cpu_baseline"] = dict(value=res["sample_d"] / best, unit="params/s", cores=res["threads"], kind="port",
+                                sample=f"best of 3 calls of oracle/refcost.py ({gar}, n={n}, f={f}) on d={res['sample_d']} columns", ms_per_call=best * 1e3)
+    # the same operator sequence on CUDA tensors ("PyTorch on B200" incumbent)
+    try:
+      from oracle import refcost
+      for _ in range(2):
+        refcost.run(gar, inputs[0], f=f)
+      torch.cuda.synchronize()
+      t0 = time.perf_counter()
+      for k in range(5):
+        refcost.run(gar, inputs[k % sets], f=f)
+      torch.cuda.synchronize()
+      line["torch_cuda_baseline"] = dict(ms_per_call=(time.perf_counter() - t0) / 5 * 1e3, what="oracle/refcost.py on CUDA tensors (library kernels)")
+    except Exception as err:
+      line["torch_cuda_baseline"] = dict(error=str(err)[:200])
+    if not args.no_sweep:
+      line["sweep"] = sweep(torch, bz, device, peak)
+  if rank == 0:
+    print(json.dumps(line), flush=True)
+  if dist is not None:
+    dist.destroy_process_group()
+
+def sweep(torch, bz, device, peak):
+  """ Kernel-level numbers for the other rules / sizes (single GPU; not part of `value`). """
+  rows_out = []
+  flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=device)
+  plan = [(25, 10, 79_510), (25, 10, 1_310_922), (25, 10, 36_489_290), (11, 5, 79_510), (11, 3, 1_310_922), (51, 12, 4_568_373)]
+  for n, f, d in plan:
+    gen = torch.Generator(device=device).manual_seed(5)
+    rows = [torch.randn(d, device=device, generator=gen) for _ in range(n)]
+    gars = ["average", "median", "trmean", "phocas", "meamed", "krum", "bulyan", "aksel", "cge"]
+    if n <= 11:
+      gars.append("brute")
+    for gar in gars:
+      ff = default_f(gar, n, f)
+      if gar == "bulyan" and n < 4 * ff + 3:
+        continue
+      fn = lambda: bz.gars[gar].unchecked(gradients=rows, f=ff)
+      try:
+        for _ in range(3):
+          fn()
+        torch.cuda.synchronize()
+        times = []
+        for _ in range(7 if d > 4e6 else 15):
+          if n * d * 4 < 4 * L2_BYTES:
+            flush.zero_()
+          a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+          a.record(); fn(); b.record()
+          torch.cuda.synchronize()
+          times.append(a.elapsed_time(b))
+        times.sort()
+        ms = times[len(times) // 2]
+        alg = algorithmic_bytes(gar, n, ff, d)
+        rows_out.append(dict(gar=gar, n=n, f=ff, d=d, ms=ms, params_per_s=d / (ms * 1e-3), gbs=alg / (ms * 1e-3) / 1e9,
+                             frac=alg / (ms * 1e-3) / 1e9 / peak, read_only_frac=n * d * 4 / (ms * 1e-3) / 1e9 / peak))
+      except Exception as err:
+        rows_out.append(dict(gar=gar, n=n, f=ff, d=d, error=str(err)[:200]))
+    del rows
+    torch.cuda.empty_cache()
+  return rows_out
+
+def main():
+  ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=200)
+  ap.add_argument("--warmup", type=int, default=10)
+  ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
+  ap.add_argument("--gar", default="trmean")
+  ap.add_argument("--n", type=int, default=25)
+  ap.add_argument("--f", type=int, default=10)
+  ap.add_argument("--d", type=int, default=1_310_922)
+  ap.add_argument("--no-sweep", action="store_true")
+  args = ap.parse_args()
+  if args.impl == "reference":
+    run_reference(args)
+  else:
+    run_b200(args)
+
+if __name__ == "__main__":
+  main()

@@ -14,9 +14,9 @@ Importing this package never touches CUDA; the compiled library is loaded on fir
 its absence is an error (no CPU fallback).
 """
 
-from . import _lib, engine, gars as _gars, plugin
+from . import _lib, engine, gars as _gars, plugin, sharded
 from .gars import gars, make_gar, register, UserException, last_selection
 from .engine import config
 
-__all__ = ["gars", "make_gar", "register", "UserException", "last_selection", "config", "engine", "plugin"]
+__all__ = ["gars", "make_gar", "register", "UserException", "last_selection", "config", "engine", "plugin", "sharded"]
 __version__ = "0.1.0"

@@ -26,21 +26,19 @@ int check_launch(const char* what) {
   return BZ_OK;
 }
 
-Split make_split(const float* const* rows, int n, const void* out, const void* extra, int64_t d, int want_vec) {
-  Split s{1, 0, d, 0};
-  if (want_vec <= 1 || d < want_vec) return s;
+Geom make_geom(const float* const* rows, int n, const void* out, const void* extra, int64_t d, int want_vec) {
+  Geom g{d, d, 0, 1};
+  if (want_vec <= 1 || d < 1) return g;
   const uintptr_t bytes = (uintptr_t)want_vec * sizeof(float);
   const uintptr_t mis = (uintptr_t)rows[0] % bytes;
-  bool same = ((uintptr_t)out % bytes) == mis && (mis % sizeof(float)) == 0;
+  bool same = ((uintptr_t)out % bytes) == mis;
   if (extra != nullptr) same = same && ((uintptr_t)extra % bytes) == mis;
   for (int r = 1; r < n && same; ++r) same = ((uintptr_t)rows[r] % bytes) == mis;
-  if (!same) return s;
-  s.vec = want_vec;
-  s.head = (int64_t)(((bytes - mis) % bytes) / sizeof(float));
-  if (s.head > d) s.head = d;
-  s.nvec = (d - s.head) / want_vec;
-  s.tail = d - s.head - s.nvec * want_vec;
-  return s;
+  if (!same) return g;
+  g.vec = want_vec;
+  g.shift = (int)(mis / sizeof(float));        // element e sits at (e + shift) modulo VEC
+  g.nv = (d + g.shift + want_vec - 1) / want_vec;
+  return g;
 }
 
 static int check_rows(const float* const* rows, int n, int64_t d, const void* out, const char* who) {
@@ -64,41 +62,28 @@ static void fill_table(RowTable& t, const float* const* rows, int n) {
   for (int r = n; r < kMaxN; ++r) t.p[r] = rows[0];
 }
 
-static Span body_span(const Split& s) { return Span{s.head, s.nvec, 0, 0}; }
-static Span edge_span(const Split& s) { return Span{0, s.head, s.head + s.nvec * s.vec, s.tail}; }
-
-static bool launch_median(int n, int vec, const RowTable& t, const Span& sp, float* out, cudaStream_t st) {
-  return launch_median_part0(n, vec, t, sp, out, st) || launch_median_part1(n, vec, t, sp, out, st) ||
-         launch_median_part2(n, vec, t, sp, out, st) || launch_median_part3(n, vec, t, sp, out, st);
+static bool launch_median(int n, const RowTable& t, const Geom& g, float* out, cudaStream_t st) {
+  return launch_median_part0(n, t, g, out, st) || launch_median_part1(n, t, g, out, st) ||
+         launch_median_part2(n, t, g, out, st) || launch_median_part3(n, t, g, out, st);
 }
-static bool launch_sorted(int n, int vec, const RowTable& t, const Span& sp, int mode, int f, float* out, cudaStream_t st) {
-  return launch_sorted_part4(n, vec, t, sp, mode, f, out, st) || launch_sorted_part5(n, vec, t, sp, mode, f, out, st) ||
-         launch_sorted_part6(n, vec, t, sp, mode, f, out, st) || launch_sorted_part7(n, vec, t, sp, mode, f, out, st);
+static bool launch_sorted(int n, const RowTable& t, const Geom& g, int mode, int f, float* out, cudaStream_t st) {
+  return launch_sorted_part4(n, t, g, mode, f, out, st) || launch_sorted_part5(n, t, g, mode, f, out, st) ||
+         launch_sorted_part6(n, t, g, mode, f, out, st) || launch_sorted_part7(n, t, g, mode, f, out, st);
 }
 
 int run_median(const float* const* rows, int n, int64_t d, float* out, cudaStream_t st) {
   RowTable t;
   fill_table(t, rows, n);
-  const Split s = make_split(rows, n, out, nullptr, d, body_vec(n));
-  if (s.vec > 1) {
-    launch_median(n, s.vec, t, body_span(s), out, st);
-    if (s.head + s.tail > 0) launch_median(n, 1, t, edge_span(s), out, st);
-  } else {
-    launch_median(n, 1, t, Span{0, d, 0, 0}, out, st);
-  }
+  launch_median(n, t, make_geom(rows, n, out, nullptr, d, body_vec(n)), out, st);
   return check_launch("k1_median");
 }
 
 int run_sorted(const float* const* rows, int n, int mode, int f, int64_t d, float* out, cudaStream_t st) {
   RowTable t;
   fill_table(t, rows, n);
-  const Split s = make_split(rows, n, out, nullptr, d, body_vec(n));
-  if (s.vec > 1) {
-    launch_sorted(n, s.vec, t, body_span(s), mode, f, out, st);
-    if (s.head + s.tail > 0) launch_sorted(n, 1, t, edge_span(s), mode, f, out, st);
-  } else {
-    launch_sorted(n, 1, t, Span{0, d, 0, 0}, mode, f, out, st);
-  }
+  const Geom g = make_geom(rows, n, out, nullptr, d, body_vec(n));
+  if (!(mode == kModeTrmean && launch_trmean_special(n, f, t, g, out, st)))
+    launch_sorted(n, t, g, mode, f, out, st);
   return check_launch("k1_sorted");
 }
 
@@ -106,13 +91,7 @@ int run_average_selected(const float* const* rows, int n, const int32_t* sel, in
                          float divisor, const int32_t* status, int64_t d, float* out, cudaStream_t st) {
   RowTable t;
   fill_table(t, rows, n);
-  const Split s = make_split(rows, n, out, nullptr, d, 4);
-  if (s.vec > 1) {
-    launch_average(s.vec, t, body_span(s), sel, count, zero_init, divisor, status, out, st);
-    if (s.head + s.tail > 0) launch_average(1, t, edge_span(s), sel, count, zero_init, divisor, status, out, st);
-  } else {
-    launch_average(1, t, Span{0, d, 0, 0}, sel, count, zero_init, divisor, status, out, st);
-  }
+  launch_average(t, make_geom(rows, n, out, nullptr, d, 4), sel, count, zero_init, divisor, status, out, st);
   return check_launch("k3_average");
 }
 

@@ -21,22 +21,20 @@ struct RowTable {
   const float* p[kMaxN];
 };
 
-// Element ranges a launch covers.  A vectorised launch covers [base0, base0 + cnt0*VEC); the
-// scalar "edges" launch covers the unaligned head [base0, base0+cnt0) and tail [base1, base1+cnt1).
-struct Span {
-  int64_t base0, cnt0, base1, cnt1;
+// Geometry of a launch over d coordinates with VEC per thread.  All rows (and the output)
+// share the same misalignment, so shifting the element index by `shift` (0..VEC-1) makes every
+// interior vector naturally aligned: logical vector v covers elements [v*VEC - shift,
+// v*VEC - shift + VEC) clipped to [0, d).  Only the first and the last vector can be partial;
+// they take a scalar load/store path inside the SAME launch (no separate edge kernel).
+struct Geom {
+  int64_t d;       // coordinates
+  int64_t nv;      // logical vectors = ceil((d + shift) / VEC)
+  int     shift;   // leading pad, in elements
+  int     vec;     // VEC of the launch (host side bookkeeping)
 };
 
-// How a [d]-long set of rows splits into an aligned vector body plus scalar edges.
-struct Split {
-  int     vec;     // 4, 2 or 1 elements per thread in the body
-  int64_t head;    // scalar elements before the body
-  int64_t nvec;    // vectors in the body
-  int64_t tail;    // scalar elements after the body
-};
-
-// Body vector width: all rows (and out) must share the same misalignment modulo the vector size.
-Split make_split(const float* const* rows, int n, const void* out, const void* extra, int64_t d, int want_vec);
+// Widest usable vector (want_vec, else 1) for these rows / output / optional extra pointer.
+Geom make_geom(const float* const* rows, int n, const void* out, const void* extra, int64_t d, int want_vec);
 
 // Error plumbing (api.cu)
 int  fail(int code, const char* fmt, ...);
@@ -70,10 +68,56 @@ template <> struct VecLoad<1> {
   static __device__ __forceinline__ void store(float* p, const float (&o)[1]) { __stcs(p, o[0]); }
 };
 
-// First element handled by logical thread i of a launch over `s` with VEC elements per thread.
+// Load the N x VEC values of the logical vector starting at element e0 of every row.  The
+// full / partial decision is taken ONCE around the whole batch so that the N loads of the
+// common (full) case stay back to back in the instruction stream (one branch, N independent
+// LDG in flight).  Partial vectors (e0 < 0 or e0 + VEC > d) read out-of-range lanes as 0.
+template <int N, int VEC>
+__device__ __forceinline__ void load_rows(const RowTable& rows, int64_t e0, int64_t d, bool full, float (&x)[VEC][N]) {
+  if (full) {
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+      float t[VEC];
+      VecLoad<VEC>::load(rows.p[r] + e0, t);
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) x[c][r] = t[c];
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) {
+        const int64_t e = e0 + c;
+        x[c][r] = (e >= 0 && e < d) ? __ldcs(rows.p[r] + e) : 0.f;
+      }
+    }
+  }
+}
+
+// Single-row variant (K3): same semantics.
 template <int VEC>
-__device__ __forceinline__ int64_t span_element(const Span& s, int64_t i) {
-  return (i < s.cnt0) ? s.base0 + i * VEC : s.base1 + (i - s.cnt0) * VEC;
+__device__ __forceinline__ void load_vec(const float* row, int64_t e0, int64_t d, bool full, float (&o)[VEC]) {
+  if (full) {
+    VecLoad<VEC>::load(row + e0, o);
+  } else {
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+      const int64_t e = e0 + c;
+      o[c] = (e >= 0 && e < d) ? __ldcs(row + e) : 0.f;
+    }
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void store_vec(float* out, int64_t e0, int64_t d, bool full, const float (&o)[VEC]) {
+  if (full) {
+    VecLoad<VEC>::store(out + e0, o);
+  } else {
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+      const int64_t e = e0 + c;
+      if (e >= 0 && e < d) __stcs(out + e, o[c]);
+    }
+  }
 }
 
 // Compare-exchange policies for SortNet<N>::run<Ops>().

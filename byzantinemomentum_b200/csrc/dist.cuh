@@ -45,6 +45,6 @@ void launch_rowdist_select(const double* parts, int nparts, int n, int sqrt_norm
 
 // ---- K4: Bulyan stage 1 means + coordinate-wise averaged median ----------------------------------
 bool launch_bulyan_reduce(const RowTable& rows, int n, int f, int m, const int32_t* order, const int32_t* status,
-                          const Span& span, float* out, cudaStream_t st);
+                          int64_t d, float* out, cudaStream_t st);
 
 }  // namespace bz

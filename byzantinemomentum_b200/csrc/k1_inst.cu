@@ -1,11 +1,11 @@
 // k1_inst.cu — instantiations of the K1 kernels for a range of n, compiled once per part
-// (`-DBZ_PART=<0..7>`) so that the 256 kernels build in parallel.  Parts 0-3: k1_median for
-// n in 1-16 / 17-32 / 33-48 / 49-64; parts 4-7: k1_sorted for the same ranges.
+// (`-DBZ_PART=<0..8>`) so that the kernels build in parallel.  Parts 0-3: k1_median for n in
+// 1-16 / 17-32 / 33-48 / 49-64; parts 4-7: generic k1_sorted for the same ranges; part 8:
+// trimmed mean with (n, f) fixed at compile time for the reference's experiment grids.
 #include "k1_select.cuh"
-#include "launch.cuh"
 
 #ifndef BZ_PART
-#error "compile with -DBZ_PART=<0..7>"
+#error "compile with -DBZ_PART=<0..8>"
 #endif
 
 #if (BZ_PART % 4) == 0
@@ -27,18 +27,48 @@ static inline unsigned blocks_for(int64_t threads) {
 #if BZ_PART < 4
 
 template <int N>
-static void launch_median_n(int vec, const RowTable& rows, const Span& span, float* out, cudaStream_t st) {
-  const int64_t threads = span.cnt0 + span.cnt1;
-  if (threads <= 0) return;
-  if (vec == 1) k1_median<N, 1><<<blocks_for(threads), kK1Threads, 0, st>>>(rows, span, out);
-  else          k1_median<N, body_vec(N)><<<blocks_for(threads), kK1Threads, 0, st>>>(rows, span, out);
+static void launch_median_n(const RowTable& rows, const Geom& g, float* out, cudaStream_t st) {
+  if (g.nv <= 0) return;
+  if (g.vec == 1) k1_median<N, 1><<<blocks_for(g.nv), kK1Threads, 0, st>>>(rows, g, out);
+  else            k1_median<N, body_vec(N)><<<blocks_for(g.nv), kK1Threads, 0, st>>>(rows, g, out);
 }
 
 #define BZ_FN2(p) launch_median_part##p
 #define BZ_FN(p) BZ_FN2(p)
-bool BZ_FN(BZ_PART)(int n, int vec, const RowTable& rows, const Span& span, float* out, cudaStream_t st) {
+bool BZ_FN(BZ_PART)(int n, const RowTable& rows, const Geom& g, float* out, cudaStream_t st) {
   switch (n) {
-#define X(N) case N: launch_median_n<N>(vec, rows, span, out, st); return true;
+#define X(N) case N: launch_median_n<N>(rows, g, out, st); return true;
+    BZ_N_LIST
+#undef X
+    default: return false;
+  }
+}
+
+#elif BZ_PART < 8
+
+template <int N, int VEC>
+static void launch_sorted_nv(const RowTable& rows, const Geom& g, int mode, int f, float* out, cudaStream_t st) {
+  if (g.nv <= 0) return;
+  size_t smem = 0;
+  if (mode != kModeTrmean) {
+    smem = (size_t)N * VEC * kK1Threads * sizeof(float);
+    static unsigned long long opted = 0;   // per instantiation, one bit per device
+    opt_in_smem(k1_sorted<N, VEC, -1, -1>, smem, opted);
+  }
+  k1_sorted<N, VEC, -1, -1><<<blocks_for(g.nv), kK1Threads, smem, st>>>(rows, g, mode, f, out);
+}
+
+template <int N>
+static void launch_sorted_n(const RowTable& rows, const Geom& g, int mode, int f, float* out, cudaStream_t st) {
+  if (g.vec == 1) launch_sorted_nv<N, 1>(rows, g, mode, f, out, st);
+  else            launch_sorted_nv<N, body_vec(N)>(rows, g, mode, f, out, st);
+}
+
+#define BZ_FN2(p) launch_sorted_part##p
+#define BZ_FN(p) BZ_FN2(p)
+bool BZ_FN(BZ_PART)(int n, const RowTable& rows, const Geom& g, int mode, int f, float* out, cudaStream_t st) {
+  switch (n) {
+#define X(N) case N: launch_sorted_n<N>(rows, g, mode, f, out, st); return true;
     BZ_N_LIST
 #undef X
     default: return false;
@@ -47,34 +77,22 @@ bool BZ_FN(BZ_PART)(int n, int vec, const RowTable& rows, const Span& span, floa
 
 #else
 
-template <int N, int VEC>
-static void launch_sorted_nv(const RowTable& rows, const Span& span, int mode, int f, float* out, cudaStream_t st) {
-  const int64_t threads = span.cnt0 + span.cnt1;
-  if (threads <= 0) return;
-  size_t smem = 0;
-  if (mode != kModeTrmean) {
-    smem = (size_t)N * VEC * kK1Threads * sizeof(float);
-    static unsigned long long opted = 0;   // per instantiation, one bit per device
-    opt_in_smem(k1_sorted<N, VEC>, smem, opted);
-  }
-  k1_sorted<N, VEC><<<blocks_for(threads), kK1Threads, smem, st>>>(rows, span, mode, f, out);
+// (n, f) of BASELINE.json's configs and of the reference's grids (reproduce.py:122-209,
+// reproduce-appendix.py:122-158): trimmed mean with the network pruned at compile time.
+#define BZ_NF_LIST Y(11, 2) Y(11, 4) Y(11, 5) Y(25, 5) Y(25, 10) Y(25, 11) Y(51, 12) Y(51, 24)
+
+template <int N, int F>
+static void launch_trmean_nf(const RowTable& rows, const Geom& g, float* out, cudaStream_t st) {
+  if (g.nv <= 0) return;
+  k1_sorted<N, body_vec(N), F, kModeTrmean><<<blocks_for(g.nv), kK1Threads, 0, st>>>(rows, g, kModeTrmean, F, out);
 }
 
-template <int N>
-static void launch_sorted_n(int vec, const RowTable& rows, const Span& span, int mode, int f, float* out, cudaStream_t st) {
-  if (vec == 1) launch_sorted_nv<N, 1>(rows, span, mode, f, out, st);
-  else          launch_sorted_nv<N, body_vec(N)>(rows, span, mode, f, out, st);
-}
-
-#define BZ_FN2(p) launch_sorted_part##p
-#define BZ_FN(p) BZ_FN2(p)
-bool BZ_FN(BZ_PART)(int n, int vec, const RowTable& rows, const Span& span, int mode, int f, float* out, cudaStream_t st) {
-  switch (n) {
-#define X(N) case N: launch_sorted_n<N>(vec, rows, span, mode, f, out, st); return true;
-    BZ_N_LIST
-#undef X
-    default: return false;
-  }
+bool launch_trmean_special(int n, int f, const RowTable& rows, const Geom& g, float* out, cudaStream_t st) {
+  if (g.vec == 1) return false;   // unaligned rows take the generic scalar kernel
+#define Y(N, F) if (n == N && f == F) { launch_trmean_nf<N, F>(rows, g, out, st); return true; }
+  BZ_NF_LIST
+#undef Y
+  return false;
 }
 
 #endif

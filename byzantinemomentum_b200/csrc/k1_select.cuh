@@ -5,8 +5,13 @@
 // keeps them in registers and runs a literal-index sorting network on them — no shared
 // memory, no stack of the n rows (the `torch.stack` of median.py:39 / trmean.py:79 is gone).
 //
-//   k1_median<N, VEC>   median.py:31-39        FMNMX.NAN network, pruned to one output rank
-//   k1_sorted<N, VEC>   trmean.py:24-50,69-109 full sort, then trmean / phocas / meamed epilogue
+//   k1_median<N, VEC>            median.py:31-39        FMNMX.NAN network, pruned to one rank
+//   k1_sorted<N, VEC, F, MODE>   trmean.py:24-50,69-109 sort, then trmean / phocas / meamed
+//
+// F / MODE = -1 mean "run-time value": one generic kernel per (N, VEC) serves every f and the
+// three epilogues after a full sort.  For the (n, f) pairs of the reference's experiment
+// grids the trimmed mean is also instantiated with F and MODE fixed: the compiler's dead-code
+// elimination then prunes the network to the comparators ranks f..n-f-1 depend on.
 //
 // Roofline: HBM (n·4 B read + 4 B written per coordinate); secondary bound: the ALU pipe
 // (FMNMX issues at 64 lanes/clk/SM): see DESIGN.md for the per-N operation counts.
@@ -24,32 +29,27 @@ constexpr int kK1Threads = 128;
 
 template <int N, int VEC>
 __global__ void __launch_bounds__(kK1Threads)
-k1_median(const __grid_constant__ RowTable rows, const Span span, float* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * kK1Threads + threadIdx.x;
-  if (i >= span.cnt0 + span.cnt1) return;
-  const int64_t e = span_element<VEC>(span, i);
-  float v[VEC][N];
-#pragma unroll
-  for (int r = 0; r < N; ++r) {
-    float t[VEC];
-    VecLoad<VEC>::load(rows.p[r] + e, t);
-#pragma unroll
-    for (int c = 0; c < VEC; ++c) v[c][r] = t[c];
-  }
+k1_median(const __grid_constant__ RowTable rows, const Geom g, float* __restrict__ out) {
+  const int64_t v = (int64_t)blockIdx.x * kK1Threads + threadIdx.x;
+  if (v >= g.nv) return;
+  const int64_t e0 = v * VEC - g.shift;
+  const bool full = e0 >= 0 && e0 + VEC <= g.d;
+  float x[VEC][N];
+  load_rows<N, VEC>(rows, e0, g.d, full, x);
   float res[VEC];
 #pragma unroll
   for (int c = 0; c < VEC; ++c) {
-    SortNet<N>::template run<OpsNaNProp>(v[c]);
-    res[c] = v[c][(N - 1) / 2];   // lower median; every other output is dead code
+    SortNet<N>::template run<OpsNaNProp>(x[c]);
+    res[c] = x[c][(N - 1) / 2];   // lower median; every other output is dead code
   }
-  VecLoad<VEC>::store(out + e, res);
+  store_vec<VEC>(out, e0, g.d, full, res);
 }
 
 // ---- trimmed mean of a sorted column (trmean.py:33) -----------------------------------------
 // `values[f:-f].mean(dim=0)`: ATen sums rows in a cascade of 16-row blocks (sequential when
 // R = n - 2f <= 16), then divides by R with one IEEE division.
 template <int N>
-__device__ __forceinline__ float trmean_sorted(const float (&s)[N], int f) {
+__device__ __forceinline__ float trmean_sorted(const float (&s)[N], const int f) {
   const int R = N - 2 * f;
   const int hi = N - f;
   float acc0 = 0.f;
@@ -72,8 +72,8 @@ __device__ __forceinline__ float trmean_sorted(const float (&s)[N], int f) {
 
 // ---- mean of the m values closest to c (trmean.py:35-50) -------------------------------------
 // In a sorted column the m closest values form a window [l, l+m).  It always holds the core
-// [R, m) (R = count - m removals) when m >= R, and of each pair (s[l], s[l+m]), l < R, the
-// closer one.  NaN distances count as largest (`topk(largest=False)`); a NaN centre gives NaN.
+// [R, m) (R = N - m removals) when m >= R, and of each pair (s[l], s[l+m]), l < R, the closer
+// one.  NaN distances count as largest (`topk(largest=False)`); a NaN centre gives NaN.
 // The partner index l+m is run-time uniform, so the sorted column is staged in shared
 // memory (`col`, stride `stride` floats between consecutive ranks).
 template <int N>
@@ -93,59 +93,64 @@ __device__ __forceinline__ float closest_pairs(const float (&s)[N], int m, float
   return (c != c) ? quiet_nan() : r;
 }
 
-template <int N, int VEC>
+template <int N, int VEC, int F, int MODE>
 __global__ void __launch_bounds__(kK1Threads)
-k1_sorted(const __grid_constant__ RowTable rows, const Span span, const int mode, const int f,
+k1_sorted(const __grid_constant__ RowTable rows, const Geom g, const int mode_rt, const int f_rt,
           float* __restrict__ out) {
   extern __shared__ float smem[];   // closest modes only: [N][VEC][kK1Threads]
-  const int64_t i = (int64_t)blockIdx.x * kK1Threads + threadIdx.x;
-  if (i >= span.cnt0 + span.cnt1) return;
-  const int64_t e = span_element<VEC>(span, i);
-  float v[VEC][N];
+  const int mode = (MODE >= 0) ? MODE : mode_rt;
+  const int f = (F >= 0) ? F : f_rt;
+  const int64_t v = (int64_t)blockIdx.x * kK1Threads + threadIdx.x;
+  if (v >= g.nv) return;
+  const int64_t e0 = v * VEC - g.shift;
+  const bool full = e0 >= 0 && e0 + VEC <= g.d;
+  float x[VEC][N];
+  load_rows<N, VEC>(rows, e0, g.d, full, x);
   float chk = 0.f;
 #pragma unroll
-  for (int r = 0; r < N; ++r) {
-    float t[VEC];
-    VecLoad<VEC>::load(rows.p[r] + e, t);
+  for (int r = 0; r < N; ++r)
 #pragma unroll
-    for (int c = 0; c < VEC; ++c) {
-      v[c][r] = t[c];
-      chk = fmaf(t[c], 0.f, chk);   // NaN iff some value is NaN or +-inf (FMA pipe, off the ALU pipe)
-    }
-  }
+    for (int c = 0; c < VEC; ++c)
+      chk = fmaf(x[c][r], 0.f, chk);   // NaN iff some value is NaN or +-inf (FMA pipe, off the ALU pipe)
+  float res[VEC];
   if (chk == chk) {
     // Fast path: all finite, plain FMNMX network
 #pragma unroll
-    for (int c = 0; c < VEC; ++c) SortNet<N>::template run<OpsFast>(v[c]);
+    for (int c = 0; c < VEC; ++c) {
+      SortNet<N>::template run<OpsFast>(x[c]);
+      if (MODE == kModeTrmean) res[c] = trmean_sorted<N>(x[c], f);
+    }
   } else {
     // Non-finite values present: sort integer keys so that NaN sorts last and +-inf keep their place
 #pragma unroll
     for (int c = 0; c < VEC; ++c) {
       int k[N];
 #pragma unroll
-      for (int r = 0; r < N; ++r) k[r] = float_to_key(v[c][r]);
+      for (int r = 0; r < N; ++r) k[r] = float_to_key(x[c][r]);
       SortNet<N>::template run<OpsKey>(k);
 #pragma unroll
-      for (int r = 0; r < N; ++r) v[c][r] = key_to_float(k[r]);
+      for (int r = 0; r < N; ++r) x[c][r] = key_to_float(k[r]);
+      if (MODE == kModeTrmean) res[c] = trmean_sorted<N>(x[c], f);
     }
   }
-  float res[VEC];
+  if (MODE != kModeTrmean) {
 #pragma unroll
-  for (int c = 0; c < VEC; ++c) {
-    if (mode == kModeTrmean) {
-      res[c] = trmean_sorted<N>(v[c], f);
-    } else {
-      float center;
-      if (mode == kModePhocas) {
-        center = trmean_sorted<N>(v[c], f);
+    for (int c = 0; c < VEC; ++c) {
+      if (mode == kModeTrmean) {
+        res[c] = trmean_sorted<N>(x[c], f);
       } else {
-        // lower median; NaN sorts last, so a NaN anywhere shows in the last rank (median.py:39)
-        center = (v[c][N - 1] != v[c][N - 1]) ? quiet_nan() : v[c][(N - 1) / 2];
+        float center;
+        if (mode == kModePhocas) {
+          center = trmean_sorted<N>(x[c], f);
+        } else {
+          // lower median; NaN sorts last, so a NaN anywhere shows in the last rank (median.py:39)
+          center = (x[c][N - 1] != x[c][N - 1]) ? quiet_nan() : x[c][(N - 1) / 2];
+        }
+        res[c] = closest_pairs<N>(x[c], N - f, center, smem + c * kK1Threads + threadIdx.x, VEC * kK1Threads);
       }
-      res[c] = closest_pairs<N>(v[c], N - f, center, smem + c * kK1Threads + threadIdx.x, VEC * kK1Threads);
     }
   }
-  VecLoad<VEC>::store(out + e, res);
+  store_vec<VEC>(out, e0, g.d, full, res);
 }
 
 }  // namespace bz

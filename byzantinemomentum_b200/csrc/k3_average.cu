@@ -13,25 +13,17 @@ namespace bz {
 constexpr int kK3Threads = 256;
 constexpr int kK3Unroll = 8;
 
-template <int VEC>
-__global__ void __launch_bounds__(kK3Threads)
-k3_average(const __grid_constant__ RowTable rows, const Span span, const int32_t* __restrict__ sel,
-           const int count, const int zero_init, const float divisor,
-           const int32_t* __restrict__ status, float* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * kK3Threads + threadIdx.x;
-  if (i >= span.cnt0 + span.cnt1) return;
-  const int64_t e = span_element<VEC>(span, i);
+// FULL: the whole vector lies inside [0, d) and is naturally aligned (the common case, kept
+// free of per-load branches so that kK3Unroll loads stay in flight); otherwise element-wise.
+template <int VEC, bool FULL>
+__device__ __forceinline__ void average_body(const RowTable& rows, const int64_t e0, const int64_t d,
+                                             const int32_t* __restrict__ sel, const int count, const int zero_init,
+                                             const float divisor, float* __restrict__ out) {
   float acc[VEC];
-  if (status != nullptr && *status != 0) {
-#pragma unroll
-    for (int c = 0; c < VEC; ++c) acc[c] = quiet_nan();
-    VecLoad<VEC>::store(out + e, acc);
-    return;
-  }
   {
     const int r0 = sel ? sel[0] : 0;
     float t[VEC];
-    VecLoad<VEC>::load(rows.p[r0] + e, t);
+    load_vec<VEC>(rows.p[r0], e0, d, FULL, t);
 #pragma unroll
     for (int c = 0; c < VEC; ++c) acc[c] = zero_init ? __fadd_rn(0.f, t[c]) : t[c];
   }
@@ -41,7 +33,7 @@ k3_average(const __grid_constant__ RowTable rows, const Span span, const int32_t
 #pragma unroll
     for (int u = 0; u < kK3Unroll; ++u) {
       const int r = sel ? sel[k + u] : k + u;
-      VecLoad<VEC>::load(rows.p[r] + e, t[u]);
+      load_vec<VEC>(rows.p[r], e0, d, FULL, t[u]);
     }
 #pragma unroll
     for (int u = 0; u < kK3Unroll; ++u)
@@ -51,23 +43,42 @@ k3_average(const __grid_constant__ RowTable rows, const Span span, const int32_t
   for (; k < count; ++k) {
     const int r = sel ? sel[k] : k;
     float t[VEC];
-    VecLoad<VEC>::load(rows.p[r] + e, t);
+    load_vec<VEC>(rows.p[r], e0, d, FULL, t);
 #pragma unroll
     for (int c = 0; c < VEC; ++c) acc[c] = __fadd_rn(acc[c], t[c]);
   }
 #pragma unroll
   for (int c = 0; c < VEC; ++c) acc[c] = __fdiv_rn(acc[c], divisor);
-  VecLoad<VEC>::store(out + e, acc);
+  store_vec<VEC>(out, e0, d, FULL, acc);
 }
 
-void launch_average(int vec, const RowTable& rows, const Span& span, const int32_t* sel, int count,
+template <int VEC>
+__global__ void __launch_bounds__(kK3Threads)
+k3_average(const __grid_constant__ RowTable rows, const Geom g, const int32_t* __restrict__ sel,
+           const int count, const int zero_init, const float divisor,
+           const int32_t* __restrict__ status, float* __restrict__ out) {
+  const int64_t v = (int64_t)blockIdx.x * kK3Threads + threadIdx.x;
+  if (v >= g.nv) return;
+  const int64_t e0 = v * VEC - g.shift;
+  const bool full = e0 >= 0 && e0 + VEC <= g.d;
+  if (status != nullptr && *status != 0) {
+    float nan[VEC];
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) nan[c] = quiet_nan();
+    store_vec<VEC>(out, e0, g.d, full, nan);
+    return;
+  }
+  if (full) average_body<VEC, true>(rows, e0, g.d, sel, count, zero_init, divisor, out);
+  else      average_body<VEC, false>(rows, e0, g.d, sel, count, zero_init, divisor, out);
+}
+
+void launch_average(const RowTable& rows, const Geom& g, const int32_t* sel, int count,
                     int zero_init, float divisor, const int32_t* status, float* out, cudaStream_t st) {
-  const int64_t threads = span.cnt0 + span.cnt1;
-  if (threads <= 0) return;
-  const unsigned blocks = (unsigned)((threads + kK3Threads - 1) / kK3Threads);
-  if (vec == 4)      k3_average<4><<<blocks, kK3Threads, 0, st>>>(rows, span, sel, count, zero_init, divisor, status, out);
-  else if (vec == 2) k3_average<2><<<blocks, kK3Threads, 0, st>>>(rows, span, sel, count, zero_init, divisor, status, out);
-  else               k3_average<1><<<blocks, kK3Threads, 0, st>>>(rows, span, sel, count, zero_init, divisor, status, out);
+  if (g.nv <= 0) return;
+  const unsigned blocks = (unsigned)((g.nv + kK3Threads - 1) / kK3Threads);
+  if (g.vec == 4)      k3_average<4><<<blocks, kK3Threads, 0, st>>>(rows, g, sel, count, zero_init, divisor, status, out);
+  else if (g.vec == 2) k3_average<2><<<blocks, kK3Threads, 0, st>>>(rows, g, sel, count, zero_init, divisor, status, out);
+  else                 k3_average<1><<<blocks, kK3Threads, 0, st>>>(rows, g, sel, count, zero_init, divisor, status, out);
 }
 
 }  // namespace bz

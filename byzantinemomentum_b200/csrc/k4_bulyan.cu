@@ -18,12 +18,12 @@ constexpr int kK4Threads = 128;
 
 template <int THETA>
 __global__ void __launch_bounds__(kK4Threads)
-k4_bulyan(const __grid_constant__ RowTable rows, const Span span, const int n, const int f, const int m,
+k4_bulyan(const __grid_constant__ RowTable rows, const int64_t d, const int n, const int f, const int m,
           const int32_t* __restrict__ order, const int32_t* __restrict__ status, float* __restrict__ out) {
   extern __shared__ float sm[];   // [max(m_max, THETA)][kK4Threads]
   const int64_t i = (int64_t)blockIdx.x * kK4Threads + threadIdx.x;
-  if (i >= span.cnt0 + span.cnt1) return;
-  const int64_t e = span_element<1>(span, i);
+  if (i >= d) return;
+  const int64_t e = i;
   if (status != nullptr && *status != 0) { out[e] = quiet_nan(); return; }
   float* col = sm + threadIdx.x;
   const int m_max = n - f - 2;
@@ -53,13 +53,18 @@ k4_bulyan(const __grid_constant__ RowTable rows, const Span span, const int n, c
   const float med = (last != last) ? quiet_nan() : key_to_float(key[(THETA - 1) / 2]);
 #pragma unroll
   for (int it = 0; it < THETA; ++it) col[it * kK4Threads] = key_to_float(key[it]);
+  // In the sorted column the beta closest values are a window [l, l+beta).  Moving the window
+  // from l to l+1 trades s[l] for s[l+beta]: a strict gain iff |s[l]-med| > |s[l+beta]-med|.  The
+  // distance to med is valley shaped along the sorted column, so the best window starts right
+  // after the LAST strict gain (a plateau of equal values longer than beta makes the gains
+  // non-contiguous, hence "last", not "count").  NaN distances count as largest.
   const int beta = THETA - 2 * f;
   const int R = THETA - beta;
   int lstar = 0;
   for (int l = 0; l < R; ++l) {
     const int dlo = abs_key(__fsub_rn(col[l * kK4Threads], med));
     const int dhi = abs_key(__fsub_rn(col[(l + beta) * kK4Threads], med));
-    lstar += (dlo > dhi) ? 1 : 0;
+    lstar = (dlo > dhi) ? l + 1 : lstar;
   }
   float acc = 0.f;
   for (int q = 0; q < beta; ++q) acc = __fadd_rn(acc, col[(lstar + q) * kK4Threads]);
@@ -68,22 +73,22 @@ k4_bulyan(const __grid_constant__ RowTable rows, const Span span, const int n, c
 }
 
 template <int THETA>
-static void launch_theta(const RowTable& rows, const Span& span, int n, int f, int m, const int32_t* order,
+static void launch_theta(const RowTable& rows, int64_t d, int n, int f, int m, const int32_t* order,
                          const int32_t* status, float* out, cudaStream_t st) {
-  const int64_t threads = span.cnt0 + span.cnt1;
+  const int64_t threads = d;
   if (threads <= 0) return;
   const int m_max = n - f - 2;
   const int rowsm = m_max > THETA ? m_max : THETA;
   const size_t smem = (size_t)rowsm * kK4Threads * sizeof(float);
   k4_bulyan<THETA><<<(unsigned)((threads + kK4Threads - 1) / kK4Threads), kK4Threads, smem, st>>>(
-      rows, span, n, f, m, order, status, out);
+      rows, d, n, f, m, order, status, out);
 }
 
 bool launch_bulyan_reduce(const RowTable& rows, int n, int f, int m, const int32_t* order, const int32_t* status,
-                          const Span& span, float* out, cudaStream_t st) {
+                          int64_t d, float* out, cudaStream_t st) {
   const int theta = n - 2 * f - 2;
   switch (theta) {
-#define X(T) case T: launch_theta<T>(rows, span, n, f, m, order, status, out, st); return true;
+#define X(T) case T: launch_theta<T>(rows, d, n, f, m, order, status, out, st); return true;
     X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
     X(17) X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26) X(27) X(28) X(29) X(30) X(31) X(32)
     X(33) X(34) X(35) X(36) X(37) X(38) X(39) X(40) X(41) X(42) X(43) X(44) X(45) X(46) X(47) X(48)

@@ -14,18 +14,20 @@ __host__ __device__ constexpr int body_vec(int n) { return n <= 28 ? 4 : 2; }
 // Epilogue of k1_sorted.
 enum SortedMode { kModeTrmean = 0, kModePhocas = 1, kModeMeamed = 2 };
 
-// K1 (k1_inst.cu, 8 parts).  Return false when n is outside the part's range.
-bool launch_median_part0(int n, int vec, const RowTable& rows, const Span& span, float* out, cudaStream_t st);
-bool launch_median_part1(int n, int vec, const RowTable& rows, const Span& span, float* out, cudaStream_t st);
-bool launch_median_part2(int n, int vec, const RowTable& rows, const Span& span, float* out, cudaStream_t st);
-bool launch_median_part3(int n, int vec, const RowTable& rows, const Span& span, float* out, cudaStream_t st);
-bool launch_sorted_part4(int n, int vec, const RowTable& rows, const Span& span, int mode, int f, float* out, cudaStream_t st);
-bool launch_sorted_part5(int n, int vec, const RowTable& rows, const Span& span, int mode, int f, float* out, cudaStream_t st);
-bool launch_sorted_part6(int n, int vec, const RowTable& rows, const Span& span, int mode, int f, float* out, cudaStream_t st);
-bool launch_sorted_part7(int n, int vec, const RowTable& rows, const Span& span, int mode, int f, float* out, cudaStream_t st);
+// K1 (k1_inst.cu, 9 parts).  Parts 0-7 return false when n is outside the part's range;
+// launch_trmean_special returns false when (n, f) has no compile-time specialisation.
+bool launch_median_part0(int n, const RowTable& rows, const Geom& g, float* out, cudaStream_t st);
+bool launch_median_part1(int n, const RowTable& rows, const Geom& g, float* out, cudaStream_t st);
+bool launch_median_part2(int n, const RowTable& rows, const Geom& g, float* out, cudaStream_t st);
+bool launch_median_part3(int n, const RowTable& rows, const Geom& g, float* out, cudaStream_t st);
+bool launch_sorted_part4(int n, const RowTable& rows, const Geom& g, int mode, int f, float* out, cudaStream_t st);
+bool launch_sorted_part5(int n, const RowTable& rows, const Geom& g, int mode, int f, float* out, cudaStream_t st);
+bool launch_sorted_part6(int n, const RowTable& rows, const Geom& g, int mode, int f, float* out, cudaStream_t st);
+bool launch_sorted_part7(int n, const RowTable& rows, const Geom& g, int mode, int f, float* out, cudaStream_t st);
+bool launch_trmean_special(int n, int f, const RowTable& rows, const Geom& g, float* out, cudaStream_t st);
 
 // K3 (k3_average.cu): ordered-subset average.
-void launch_average(int vec, const RowTable& rows, const Span& span, const int32_t* sel, int count,
+void launch_average(const RowTable& rows, const Geom& g, const int32_t* sel, int count,
                     int zero_init, float divisor, const int32_t* status, float* out, cudaStream_t st);
 
 // Opt a kernel into > 48 KB of dynamic shared memory once per device.

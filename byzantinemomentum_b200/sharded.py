@@ -1,0 +1,96 @@
+# coding: utf-8
+"""d-sharded aggregation across GPUs (one process per GPU, `torch.distributed`).
+
+Rank r holds the columns of its shard of every worker gradient — a list of n fp32 vectors of
+length d_r — and produces the matching shard of the aggregated gradient.
+
+  * average / median / trmean / phocas / meamed are coordinate-wise: NO collective.
+  * krum / bulyan / brute / aksel / cge select whole rows from global distances: each rank
+    computes the fp64 partial sums of squares over its shard (phase A), ONE all-gather
+    exchanges the R small blocks (n*n or n doubles per rank: 5 KB at n = 25), every rank sums
+    them in rank order — bitwise the same result everywhere, so every rank derives the
+    identical selection (phase B) — and reduces its own shard with it (phase C).
+    An all-reduce would leave the summation order to the collective; all-gather + fixed
+    order does not.
+
+The reference has no distributed path at all; this module is the new
+multi-GPU form of its `aggregate(gradients, f, ...)`.
+
+`backend` is the object providing the phases; it defaults to `byzantinemomentum_b200.engine`
+(the CUDA library).  The CPU tests inject a NumPy stand-in to exercise this host logic under
+`gloo` with world_size 2; there is no fallback: with the default backend and no GPU the
+phases raise.
+"""
+
+import torch
+import torch.distributed as dist
+
+from . import engine as _engine
+
+__all__ = ["aggregate", "COORDINATE_WISE", "DISTANCE_BASED"]
+
+COORDINATE_WISE = ("average", "median", "trmean", "phocas", "meamed")
+DISTANCE_BASED = ("krum", "bulyan", "brute", "aksel", "cge")
+
+def _gather(part, group):
+  """ All-gather one small fp64 block per rank -> [R, *part.shape], rank order. """
+  world = dist.get_world_size(group) if dist.is_initialized() else 1
+  if world == 1:
+    return part.unsqueeze(0).contiguous()
+  gathered = torch.empty((world,) + tuple(part.shape), dtype=part.dtype, device=part.device)
+  dist.all_gather([gathered[r] for r in range(world)], part.contiguous(), group=group)
+  return gathered
+
+def aggregate(gar, gradients, f=None, m=None, mode="mid", group=None, backend=None, return_selection=False):
+  """ Aggregate this rank's shard.
+  Args:
+    gar        Rule name (one of COORDINATE_WISE + DISTANCE_BASED)
+    gradients  List of n fp32 CUDA vectors: this rank's columns of the n worker gradients
+    f          Number of Byzantine gradients to tolerate (ignored by average / median)
+    m          Multi-Krum selection size (krum / bulyan; default n - f - 2)
+    mode       Aksel mode ("mid" or "n-f")
+    group      Process group (default: the world)
+    backend    Provider of the phases (default: the CUDA engine)
+  Returns:
+    This rank's shard of the aggregated gradient (and the device-side selection if asked)
+  """
+  be = backend or _engine
+  n = len(gradients)
+  if gar in COORDINATE_WISE:
+    if gar == "average":
+      out = be.average(gradients)
+    elif gar == "median":
+      out = be.median(gradients)
+    else:
+      out = getattr(be, gar)(gradients, f)
+    return (out, None) if return_selection else out
+  if gar == "krum":
+    m = n - f - 2 if m is None else m
+    parts = _gather(be.pairdist_partial(gradients), group)
+    order = be.krum_select(parts, n, f)
+    out = be.average_selected(gradients, order, m)
+    sel = order
+  elif gar == "bulyan":
+    m = n - f - 2 if m is None else m
+    parts = _gather(be.pairdist_partial(gradients), group)
+    order, status = be.bulyan_select(parts, n, f, m)
+    out = be.bulyan_reduce(gradients, f, m, order, status)
+    sel = order
+  elif gar == "brute":
+    parts = _gather(be.pairdist_partial(gradients), group)
+    sel, status = be.brute_select(parts, n, f)
+    out = be.average_selected(gradients, sel, n - f, status=status)
+  elif gar == "aksel":
+    count = (n + 1) // 2 if mode == "mid" else n - f
+    center = be.median(gradients)                                   # coordinate-wise: local
+    parts = _gather(be.rowdist_partial(gradients, center), group)
+    sel = be.rowdist_select(parts, n, False)
+    out = be.average_selected(gradients, sel, count)
+  elif gar == "cge":
+    count = n - f
+    parts = _gather(be.rowdist_partial(gradients, None), group)
+    sel = be.rowdist_select(parts, n, True)
+    out = be.average_selected(gradients, sel, count, zero_init=False)
+  else:
+    raise KeyError(f"unknown aggregation rule {gar!r}")
+  return (out, sel) if return_selection else out
