@@ -7,6 +7,8 @@ called from `attack.py:821-822`): same plugin interface, hand-written CUDA under
     from byzantinemomentum_b200 import gars
     aggregated = gars["krum"](gradients=list_of_flat_fp32_cuda_tensors, f=5)
 
+    plan = byzantinemomentum_b200.Plan("krum", gradients, f=5)   # prepared call: plan() is ~3 us of host time
+
     import aggregators                              # the unmodified reference
     byzantinemomentum_b200.plugin.install(aggregators)   # registers "b200-<name>" rules
 
@@ -16,7 +18,7 @@ its absence is an error (no CPU fallback).
 
 from . import _lib, engine, gars as _gars, plugin, sharded
 from .gars import gars, make_gar, register, UserException, last_selection
-from .engine import config
+from .engine import config, Plan
 
-__all__ = ["gars", "make_gar", "register", "UserException", "last_selection", "config", "engine", "plugin", "sharded"]
+__all__ = ["gars", "make_gar", "register", "UserException", "last_selection", "config", "Plan", "engine", "plugin", "sharded"]
 __version__ = "0.1.0"

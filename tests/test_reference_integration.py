@@ -1,0 +1,74 @@
+# coding: utf-8
+"""Drop-in registration inside the UNMODIFIED reference (build container only: skipped where
+/root/reference does not exist, e.g. on the GPU box).  Runs in a subprocess because importing
+the reference replaces sys.stdout / sys.stderr / sys.excepthook (tools/__init__.py:215-216,246)."""
+
+import os
+import pathlib
+import subprocess
+import sys
+
+import pytest
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+REF = pathlib.Path(os.environ.get("BYZ_REFERENCE", "/root/reference"))
+
+SCRIPT = r"""
+import sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {ref!r})
+out = sys.stdout
+import aggregators
+import byzantinemomentum_b200 as bz
+import torch
+res = []
+# Route 1: the reference found our top-level `native` package and registered native-<gar>
+res.append(sorted(k for k in aggregators.gars if k.startswith("native-")) == ["native-brute", "native-bulyan", "native-krum", "native-median"])
+# Route 2: register through the reference's own register()
+names = bz.plugin.install(aggregators)
+res.append(all(name in aggregators.gars for name in names) and len(names) == 10)
+rows = [torch.zeros(8) for _ in range(7)]
+# the reference's wrapper validates with OUR check functions and raises ITS UserException
+import tools
+try:
+  aggregators.gars["b200-krum"].checked(gradients=rows, f=3)
+  res.append(False)
+except tools.UserException:
+  res.append(True)
+# members the rest of the reference relies on (study.py:361-366, attack.py:822)
+rule = aggregators.gars["b200-krum"]
+res.append(rule.upper_bound(25, 5, 10) == aggregators.gars["krum"].upper_bound(25, 5, 10))
+res.append(callable(rule.influence) and aggregators.gars["b200-median"].influence is None)
+# same verdicts as the reference's own check() on a grid of (n, f, m)
+same = True
+for n in (1, 3, 7, 11, 25):
+  g = [torch.zeros(4) for _ in range(n)]
+  for f in (0, 1, 2, 3, 5, 12, "x"):
+    for name in ("trmean", "phocas", "meamed", "krum", "bulyan", "brute", "aksel", "cge", "median", "average"):
+      for extra in ({{}}, {{"m": 1}}, {{"m": 99}}, {{"mode": "n-f"}}, {{"mode": "zzz"}}):
+        try:
+          a = aggregators.gars[name].check(gradients=g, f=f, **extra)
+        except TypeError:
+          a = "TypeError"
+        try:
+          b = aggregators.gars["b200-" + name].check(gradients=g, f=f, **extra)
+        except TypeError:
+          b = "TypeError"
+        if (a is None) != (b is None):
+          same = False
+          out.write(f"check differs: {{name}} n={{n}} f={{f}} {{extra}}: {{a!r}} vs {{b!r}}\n")
+res.append(same)
+# override: --gar krum now resolves to the CUDA rule
+bz.plugin.install(aggregators, override=True, names=["krum"])
+res.append(aggregators.gars["krum"].unchecked.__module__.startswith("byzantinemomentum_b200"))
+out.write("RESULT " + " ".join(str(int(x)) for x in res) + "\n")
+out.flush()
+"""
+
+@pytest.mark.skipif(not (REF / "aggregators" / "__init__.py").exists(), reason="reference not present on this box")
+def test_rules_register_inside_the_unmodified_reference(tmp_path):
+  script = tmp_path / "drive.py"
+  script.write_text(SCRIPT.format(root=str(ROOT), ref=str(REF)))
+  proc = subprocess.run([sys.executable, str(script)], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+  lines = [l for l in proc.stdout.splitlines() if l.startswith("RESULT")]
+  assert lines, proc.stdout[-2000:] + proc.stderr[-2000:]
+  assert lines[-1] == "RESULT 1 1 1 1 1 1 1", proc.stdout[-3000:]
