@@ -120,6 +120,31 @@ __device__ __forceinline__ void store_vec(float* out, int64_t e0, int64_t d, boo
   }
 }
 
+// ---- cp.async (LDGSTS) helpers -------------------------------------------------------------
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(K) : "memory"); }
+
+// Copy VEC floats global -> shared (both naturally aligned to 4·VEC bytes).
+template <int VEC>
+__device__ __forceinline__ void cp_async_vec(float* smem, const float* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  if (VEC == 4)      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+  else if (VEC == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+  else               asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+template <int VEC>
+__device__ __forceinline__ void lds_vec(const float* smem, float (&o)[VEC]) {
+  if (VEC == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(smem);
+    o[0] = t.x; o[1] = t.y; o[VEC > 2 ? 2 : 0] = t.z; o[VEC > 3 ? 3 : 0] = t.w;
+  } else if (VEC == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(smem);
+    o[0] = t.x; o[VEC > 1 ? 1 : 0] = t.y;
+  } else {
+    o[0] = *smem;
+  }
+}
+
 // Compare-exchange policies for SortNet<N>::run<Ops>().
 // Fast: inputs hold no NaN (plain FMNMX).
 struct OpsFast {

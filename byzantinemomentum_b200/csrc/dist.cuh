@@ -13,7 +13,7 @@ namespace bz {
 // [kWsHeader, kWsHeader + n*n*8)       : reduced block (double[n*n] or double[n])
 // [.., + kMaxParts * n*n*8)            : per-CTA partial blocks of K2 / K2'
 constexpr size_t kWsHeader = 1024;
-constexpr int    kMaxParts = 160;     // >= number of CTAs K2 / K2' ever launch along x
+constexpr int    kMaxParts = 304;     // >= number of CTAs K2 / K2' ever launch along x (2 per SM)
 size_t workspace_bytes(int n);
 
 struct Workspace {
@@ -30,7 +30,8 @@ bool carve_workspace(void* ws, size_t bytes, int n, Workspace& out);
 int launch_pairdist(const RowTable& rows, int n, int64_t d, double* parts, cudaStream_t st);
 
 // K2': parts[x*n + i] = share of sum_k (rows[i][k] - center[k])^2 (center NULL: the origin).
-int launch_rowdist(const RowTable& rows, int n, const float* center, int64_t d, double* parts, cudaStream_t st);
+int launch_rowdist(const RowTable& rows, int n, const float* const* host_rows, const float* center, int64_t d,
+                   double* parts, cudaStream_t st);
 
 // Sum `nparts` blocks of `len` doubles in index order into `block` (fixed order: deterministic).
 // pair_n > 0: the block is a pair_n x pair_n table of which only entries i < j are defined; the

@@ -20,8 +20,26 @@
 
 namespace bz {
 
-static inline unsigned blocks_for(int64_t threads) {
-  return (unsigned)((threads + kK1Threads - 1) / kK1Threads);
+// Persistent grid: as many CTAs as are resident at once (occupancy x SMs), or fewer when the
+// launch has fewer tiles.  The occupancy query is cached per kernel instantiation and device.
+template <class K>
+static unsigned persistent_grid(K kernel, size_t smem, int64_t nv, int (&cache)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& resident = cache[dev & 63];
+  if (resident == 0) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0, sms = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kK1Threads, smem);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    resident = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
+  }
+  const int64_t tiles = (nv + kK1Threads - 1) / kK1Threads;
+#if BZ_K1_VARIANT == 2
+  return (unsigned)tiles;
+#else
+  return (unsigned)(tiles < resident ? tiles : resident);
+#endif
 }
 
 #if BZ_PART < 4
@@ -29,8 +47,15 @@ static inline unsigned blocks_for(int64_t threads) {
 template <int N>
 static void launch_median_n(const RowTable& rows, const Geom& g, float* out, cudaStream_t st) {
   if (g.nv <= 0) return;
-  if (g.vec == 1) k1_median<N, 1><<<blocks_for(g.nv), kK1Threads, 0, st>>>(rows, g, out);
-  else            k1_median<N, body_vec(N)><<<blocks_for(g.nv), kK1Threads, 0, st>>>(rows, g, out);
+  if (g.vec == 1) {
+    static int cache[64] = {0};
+    const size_t smem = Stage<N, 1>::kFloats * sizeof(float);
+    k1_median<N, 1><<<persistent_grid(k1_median<N, 1>, smem, g.nv, cache), kK1Threads, smem, st>>>(rows, g, out);
+  } else {
+    static int cache[64] = {0};
+    const size_t smem = Stage<N, body_vec(N)>::kFloats * sizeof(float);
+    k1_median<N, body_vec(N)><<<persistent_grid(k1_median<N, body_vec(N)>, smem, g.nv, cache), kK1Threads, smem, st>>>(rows, g, out);
+  }
 }
 
 #define BZ_FN2(p) launch_median_part##p
@@ -49,13 +74,14 @@ bool BZ_FN(BZ_PART)(int n, const RowTable& rows, const Geom& g, float* out, cuda
 template <int N, int VEC>
 static void launch_sorted_nv(const RowTable& rows, const Geom& g, int mode, int f, float* out, cudaStream_t st) {
   if (g.nv <= 0) return;
-  size_t smem = 0;
-  if (mode != kModeTrmean) {
-    smem = (size_t)N * VEC * kK1Threads * sizeof(float);
-    static unsigned long long opted = 0;   // per instantiation, one bit per device
-    opt_in_smem(k1_sorted<N, VEC, -1, -1>, smem, opted);
-  }
-  k1_sorted<N, VEC, -1, -1><<<blocks_for(g.nv), kK1Threads, smem, st>>>(rows, g, mode, f, out);
+  // stage, plus the sorted columns for the closest modes (two occupancy classes: cached apart)
+  static int cache_plain[64] = {0}, cache_closest[64] = {0};
+  const size_t stage = Stage<N, VEC>::kFloats * sizeof(float);
+  const size_t both = stage + Stage<N, VEC>::kColumnFloats * sizeof(float);
+  if (mode == kModeTrmean)
+    k1_sorted<N, VEC, -1, -1><<<persistent_grid(k1_sorted<N, VEC, -1, -1>, stage, g.nv, cache_plain), kK1Threads, stage, st>>>(rows, g, mode, f, out);
+  else
+    k1_sorted<N, VEC, -1, -1><<<persistent_grid(k1_sorted<N, VEC, -1, -1>, both, g.nv, cache_closest), kK1Threads, both, st>>>(rows, g, mode, f, out);
 }
 
 template <int N>
@@ -77,14 +103,20 @@ bool BZ_FN(BZ_PART)(int n, const RowTable& rows, const Geom& g, int mode, int f,
 
 #else
 
-// (n, f) of BASELINE.json's configs and of the reference's grids (reproduce.py:122-209,
-// reproduce-appendix.py:122-158): trimmed mean with the network pruned at compile time.
-#define BZ_NF_LIST Y(11, 2) Y(11, 4) Y(11, 5) Y(25, 5) Y(25, 10) Y(25, 11) Y(51, 12) Y(51, 24)
+// n of BASELINE.json's configs and of the reference's grids (reproduce.py:122-209,
+// reproduce-appendix.py:122-158), every valid f: trimmed mean with the network pruned at compile time.
+#define BZ_NF_LIST \
+  Y(11, 1) Y(11, 2) Y(11, 3) Y(11, 4) Y(11, 5) \
+  Y(25, 1) Y(25, 2) Y(25, 3) Y(25, 4) Y(25, 5) Y(25, 6) Y(25, 7) Y(25, 8) Y(25, 9) Y(25, 10) Y(25, 11) Y(25, 12) \
+  Y(51, 1) Y(51, 2) Y(51, 3) Y(51, 4) Y(51, 5) Y(51, 6) Y(51, 7) Y(51, 8) Y(51, 9) Y(51, 10) Y(51, 11) Y(51, 12) Y(51, 13) \
+  Y(51, 14) Y(51, 15) Y(51, 16) Y(51, 17) Y(51, 18) Y(51, 19) Y(51, 20) Y(51, 21) Y(51, 22) Y(51, 23) Y(51, 24) Y(51, 25)
 
 template <int N, int F>
 static void launch_trmean_nf(const RowTable& rows, const Geom& g, float* out, cudaStream_t st) {
   if (g.nv <= 0) return;
-  k1_sorted<N, body_vec(N), F, kModeTrmean><<<blocks_for(g.nv), kK1Threads, 0, st>>>(rows, g, kModeTrmean, F, out);
+  static int cache[64] = {0};
+  const size_t smem = Stage<N, body_vec(N)>::kFloats * sizeof(float);
+  k1_sorted<N, body_vec(N), F, kModeTrmean><<<persistent_grid(k1_sorted<N, body_vec(N), F, kModeTrmean>, smem, g.nv, cache), kK1Threads, smem, st>>>(rows, g, kModeTrmean, F, out);
 }
 
 bool launch_trmean_special(int n, int f, const RowTable& rows, const Geom& g, float* out, cudaStream_t st) {

@@ -17,6 +17,7 @@
 // rows) give bitwise identical sums.
 // Roofline: HBM n·4 B per coordinate; secondary: FP32 pipe, n(n-1) lane-ops per coordinate.
 #include "dist.cuh"
+#include "reduce.cuh"
 
 namespace bz {
 
@@ -36,8 +37,6 @@ __device__ __forceinline__ void cp_async4(float* smem, const float* gmem, int sr
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(K) : "memory"); }
 
 __device__ __forceinline__ u64 sub2(u64 a, u64 b) {
   u64 d;
@@ -113,21 +112,6 @@ __device__ __forceinline__ void sweep_tile(const float* buf, int T, const int (&
         }
     }
   }
-}
-
-// Transposed warp reduction: on return, lane L holds sum over lanes of v[L] (v has 32 slots).
-__device__ __forceinline__ float transpose_reduce(float (&v)[32], int lane) {
-#pragma unroll
-  for (int h = 16; h >= 1; h >>= 1) {
-    const bool up = (lane & h) != 0;
-#pragma unroll
-    for (int j = 0; j < h; ++j) {
-      const float send = up ? v[j] : v[j + h];
-      const float keep = up ? v[j + h] : v[j];
-      v[j] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, h));
-    }
-  }
-  return v[0];
 }
 
 template <int NP>
@@ -206,69 +190,6 @@ k2_pairdist(const __grid_constant__ RowTable rows, const int n, const int T, con
   }
 }
 
-// ---- K2': squared distance of every row to a centre --------------------------------------------
-// Warp w of a CTA owns rows w, w+16, w+32, w+48; lanes stride over the CTA's coordinates with
-// float4 loads straight from global memory (no reuse to stage).  fp32 partials over <= 32
-// terms, then per-lane fp64.
-constexpr int kRdThreads = 512;
-constexpr int kRdRows = (kMaxN + 15) / 16;   // rows per warp
-
-template <bool CENTER, int VEC>
-__global__ void __launch_bounds__(kRdThreads)
-k2_rowdist(const __grid_constant__ RowTable rows, const int n, const float* __restrict__ center,
-           const int64_t base, const int64_t nvec, double* __restrict__ parts) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double dacc[kRdRows];
-#pragma unroll
-  for (int k = 0; k < kRdRows; ++k) dacc[k] = 0.;
-  // A CTA walks chunks of 32 lanes * 8 vectors; all 16 warps of the CTA visit the same chunk
-  // (the centre is shared through L1), each on its own rows.
-  const int64_t chunk = 32 * 8;
-  for (int64_t v0 = (int64_t)blockIdx.x * chunk; v0 < nvec; v0 += (int64_t)gridDim.x * chunk) {
-    float acc[kRdRows];
-#pragma unroll
-    for (int k = 0; k < kRdRows; ++k) acc[k] = 0.f;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int64_t iv = v0 + u * 32 + lane;
-      if (iv < nvec) {
-        const int64_t e = base + iv * VEC;
-        float c[VEC];
-        if (CENTER) VecLoad<VEC>::load(center + e, c);
-#pragma unroll
-        for (int k = 0; k < kRdRows; ++k) {
-          const int r = warp + 16 * k;
-          if (r < n) {
-            float x[VEC];
-            VecLoad<VEC>::load(rows.p[r] + e, x);
-#pragma unroll
-            for (int q = 0; q < VEC; ++q) {
-              // aksel.py:41 `(x - m).pow_(2).sum()`: the square is rounded to fp32, then summed;
-              // cge.py:36 `norm()`: sum of squares, fused
-              if (CENTER) {
-                const float df = __fsub_rn(x[q], c[q]);
-                acc[k] = __fadd_rn(acc[k], __fmul_rn(df, df));
-              } else {
-                acc[k] = fmaf(x[q], x[q], acc[k]);
-              }
-            }
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < kRdRows; ++k) dacc[k] += (double)acc[k];
-  }
-#pragma unroll
-  for (int k = 0; k < kRdRows; ++k) {
-    double v = dacc[k];
-#pragma unroll
-    for (int h = 16; h >= 1; h >>= 1) v += __shfl_xor_sync(0xffffffffu, v, h);
-    const int r = warp + 16 * k;
-    if (lane == 0 && r < n) parts[(size_t)blockIdx.x * n + r] = v;
-  }
-}
-
 // ---- fixed-order reduction of partial blocks --------------------------------------------------
 __global__ void k_reduce_parts(const double* __restrict__ parts, int nparts, int len, int pair_n, double* __restrict__ block) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -317,41 +238,6 @@ int launch_pairdist(const RowTable& rows, int n, int64_t d, double* parts, cudaS
   if ((int64_t)gx > ntiles) gx = (int)(ntiles > 0 ? ntiles : 1);
   k2_pairdist<<<dim3(gx, gy > 0 ? gy : 1), kK2Threads, smem, st>>>(rows, n, T, logq, d, ntiles, parts);
   return gx;
-}
-
-int launch_rowdist(const RowTable& rows, int n, const float* center, int64_t d, double* parts, cudaStream_t st) {
-  // Vector width: every row (and the centre) must be 16-byte aligned, else scalar loads
-  bool al = true;
-  for (int r = 0; r < n && al; ++r) al = (((uintptr_t)rows.p[r]) & 15) == 0;
-  if (center != nullptr) al = al && ((((uintptr_t)center) & 15) == 0);
-  const int64_t chunk4 = 32 * 8 * 4;
-  int gx = sm_count() * 2;
-  if (gx > kMaxParts) gx = kMaxParts;
-  // Body (vectorised) + scalar tail share one partial layout: the tail is a second launch
-  // that ADDS nothing in place; instead the vector kernel covers floor(d/4)*4 elements and the
-  // scalar kernel the rest, each writing its own range of blocks.
-  const int64_t nvec4 = al ? d / 4 : 0;
-  const int64_t rest = d - nvec4 * 4;
-  int used = 0;
-  if (nvec4 > 0) {
-    int g = gx - 1;
-    const int64_t need = (nvec4 * 4 + chunk4 - 1) / chunk4;
-    if ((int64_t)g > need) g = (int)need;
-    if (g < 1) g = 1;
-    if (center) k2_rowdist<true, 4><<<g, kRdThreads, 0, st>>>(rows, n, center, 0, nvec4, parts);
-    else        k2_rowdist<false, 4><<<g, kRdThreads, 0, st>>>(rows, n, center, 0, nvec4, parts);
-    used = g;
-  }
-  if (rest > 0 || used == 0) {
-    int g = al ? 1 : gx;
-    const int64_t need = (rest + 32 * 8 - 1) / (32 * 8);
-    if ((int64_t)g > need) g = (int)(need > 0 ? need : 1);
-    if (g > kMaxParts - used) g = kMaxParts - used;
-    if (center) k2_rowdist<true, 1><<<g, kRdThreads, 0, st>>>(rows, n, center, nvec4 * 4, rest, parts + (size_t)used * n);
-    else        k2_rowdist<false, 1><<<g, kRdThreads, 0, st>>>(rows, n, center, nvec4 * 4, rest, parts + (size_t)used * n);
-    used += g;
-  }
-  return used;
 }
 
 void launch_reduce_parts(const double* parts, int nparts, int len, int pair_n, double* block, cudaStream_t st) {

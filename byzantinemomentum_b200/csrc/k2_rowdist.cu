@@ -1,0 +1,132 @@
+// k2_rowdist.cu — K2': squared distance of every row to a centre vector, in one pass over
+// the rows: the coordinate-wise median for Aksel (`(x - m).pow_(2).sum()`, aksel.py:41: the
+// square is rounded to fp32 before it is summed) or the origin for CGE (`grad.norm()`,
+// cge.py:36).  The reference makes n separate passes with a host sync each.
+//
+// One thread owns VEC adjacent coordinates and walks the rows in chunks of 8 (8 independent
+// vector loads in flight), keeping one fp32 accumulator per row in registers (64 of them: the
+// row index must be a literal).  Every 8 vectors (<= 32 terms per accumulator) the lane
+// partials are transposed-reduced over the warp (lane r ends with row r and row r+32) into
+// fp64; warps are combined through shared memory in fixed order; one fp64 block per CTA is
+// summed by K5.  Deterministic; identical rows give identical sums.
+// Roofline: HBM, n·4 B per coordinate (+4 B for the centre).
+#include "dist.cuh"
+#include "reduce.cuh"
+
+namespace bz {
+
+constexpr int kRdThreads = 256;
+constexpr int kRdWarps = kRdThreads / 32;
+constexpr int kRdChunk = 4;      // rows loaded together (4 x VEC values in flight per thread)
+constexpr int kRdFlush = 8;      // vectors between two flushes
+
+template <bool CENTER, int VEC>
+__global__ void __launch_bounds__(kRdThreads, 2)
+k2_rowdist(const __grid_constant__ RowTable rows, const int n, const float* __restrict__ center, const Geom g,
+           double* __restrict__ parts) {
+  __shared__ double warp_tot[kRdWarps][kMaxN];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[kMaxN];
+#pragma unroll
+  for (int r = 0; r < kMaxN; ++r) acc[r] = 0.f;
+  double d0 = 0., d1 = 0.;      // rows `lane` and `lane + 32`
+  const int64_t stride = (int64_t)gridDim.x * kRdThreads;
+  // warp-uniform trip count: lanes past the end contribute zeros and still join the shuffles
+  const int64_t first = (int64_t)blockIdx.x * kRdThreads + warp * 32;
+  int pending = 0;
+  for (int64_t vb = first; vb < g.nv; vb += stride) {
+    const int64_t v = vb + lane;
+    const bool live = v < g.nv;
+    const int64_t e0 = v * VEC - g.shift;
+    const bool full = live && e0 >= 0 && e0 + VEC <= g.d;
+    float c[VEC];
+    if (CENTER) {
+      if (full) VecLoad<VEC>::load(center + e0, c);
+      else {
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) { const int64_t e = e0 + q; c[q] = (live && e >= 0 && e < g.d) ? __ldcs(center + e) : 0.f; }
+      }
+    }
+#pragma unroll
+    for (int r0 = 0; r0 < kMaxN; r0 += kRdChunk) {
+      if (r0 < n) {     // uniform; rows r >= n alias row 0 in the table, their sums are discarded
+        float x[kRdChunk][VEC];
+        if (full) {
+#pragma unroll
+          for (int u = 0; u < kRdChunk; ++u) VecLoad<VEC>::load(rows.p[r0 + u] + e0, x[u]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < kRdChunk; ++u)
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) {
+              const int64_t e = e0 + q;
+              const bool ok = live && e >= 0 && e < g.d;
+              // out-of-range lanes must add exactly 0: take the centre itself
+              x[u][q] = ok ? __ldcs(rows.p[r0 + u] + e) : (CENTER ? c[q] : 0.f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kRdChunk; ++u)
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) {
+            if (CENTER) {
+              const float df = __fsub_rn(x[u][q], c[q]);
+              acc[r0 + u] = __fadd_rn(acc[r0 + u], __fmul_rn(df, df));
+            } else {
+              acc[r0 + u] = fmaf(x[u][q], x[u][q], acc[r0 + u]);
+            }
+          }
+      }
+    }
+    if (++pending == kRdFlush) {
+      pending = 0;
+      d0 += (double)transpose_reduce(*reinterpret_cast<float(*)[32]>(&acc[0]), lane);
+      if (n > 32) d1 += (double)transpose_reduce(*reinterpret_cast<float(*)[32]>(&acc[32]), lane);
+#pragma unroll
+      for (int r = 0; r < kMaxN; ++r) acc[r] = 0.f;
+    }
+  }
+  if (pending > 0) {
+    d0 += (double)transpose_reduce(*reinterpret_cast<float(*)[32]>(&acc[0]), lane);
+    if (n > 32) d1 += (double)transpose_reduce(*reinterpret_cast<float(*)[32]>(&acc[32]), lane);
+  }
+  warp_tot[warp][lane] = d0;
+  warp_tot[warp][lane + 32] = d1;
+  __syncthreads();
+  if (threadIdx.x < n) {
+    double s = 0.;
+#pragma unroll
+    for (int w = 0; w < kRdWarps; ++w) s += warp_tot[w][threadIdx.x];
+    parts[(size_t)blockIdx.x * n + threadIdx.x] = s;
+  }
+}
+
+static int rd_sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& c = cached[dev & 63];
+  if (c == 0) cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev);
+  return c > 0 ? c : 148;
+}
+
+int launch_rowdist(const RowTable& rows, int n, const float* const* host_rows, const float* center, int64_t d,
+                   double* parts, cudaStream_t st) {
+  // The centre doubles as the alignment reference ("out") of the geometry
+  const Geom g = make_geom(host_rows, n, center ? (const void*)center : (const void*)host_rows[0], nullptr, d, 4);
+  int64_t grid = (g.nv + kRdThreads - 1) / kRdThreads;
+  const int64_t cap = (int64_t)rd_sm_count() * 2;
+  if (grid > cap) grid = cap;
+  if (grid > kMaxParts) grid = kMaxParts;
+  if (grid < 1) grid = 1;
+  if (g.vec == 4) {
+    if (center) k2_rowdist<true, 4><<<(unsigned)grid, kRdThreads, 0, st>>>(rows, n, center, g, parts);
+    else        k2_rowdist<false, 4><<<(unsigned)grid, kRdThreads, 0, st>>>(rows, n, center, g, parts);
+  } else {
+    if (center) k2_rowdist<true, 1><<<(unsigned)grid, kRdThreads, 0, st>>>(rows, n, center, g, parts);
+    else        k2_rowdist<false, 1><<<(unsigned)grid, kRdThreads, 0, st>>>(rows, n, center, g, parts);
+  }
+  return (int)grid;
+}
+
+}  // namespace bz

@@ -15,26 +15,49 @@ constexpr int kK5Threads = 1024;
 
 __device__ __forceinline__ bool finite_d(double x) { return fabs(x) <= 1.7976931348623157e308; }
 
-// Sum `nparts` partial blocks in index order (bitwise reproducible on every rank).
-__device__ __forceinline__ double sum_parts(const double* __restrict__ parts, int nparts, size_t stride, size_t e) {
-  double s = 0.;
-  for (int p = 0; p < nparts; ++p) s += parts[(size_t)p * stride + e];
-  return s;
+// Block-wide, deterministic sum of `nparts` partial blocks of `len` doubles into smem `out`.
+// The parts are split in `slices` interleaved classes (p mod slices); thread (slice, t) walks
+// entries t, t + T, ... and adds its class in ascending p; the classes are then added in
+// ascending order.  The order depends only on (nparts, slices): bitwise reproducible, and the
+// same on every rank of the sharded path.  All loads of a thread are independent across
+// entries, so a thread keeps several in flight (the naive per-entry loop over 148 parts cost
+// ~20 us of pure latency).
+__device__ void block_sum_parts(const double* __restrict__ parts, int nparts, int len, int slices,
+                                double* __restrict__ scratch, double* __restrict__ out) {
+  const int T = blockDim.x / slices;            // threads per slice
+  const int slice = threadIdx.x / T, t = threadIdx.x - slice * T;
+  if (slice < slices) {
+    for (int e = t; e < len; e += T) {
+      double s = 0.;
+      for (int p = slice; p < nparts; p += slices) s += parts[(size_t)p * len + e];
+      scratch[slice * len + e] = s;
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < len; e += blockDim.x) {
+    double s = 0.;
+    for (int k = 0; k < slices; ++k) s += scratch[k * len + e];
+    out[e] = s;
+  }
+  __syncthreads();
 }
 
-// dist[i][j] = double(fl32(sqrt(sum_k (x_i - x_j)^2))); diagonal = `diag`.
-__device__ void load_distances(const double* __restrict__ parts, int nparts, int n, bool map_nonfinite, double diag,
-                               double* dist) {
+// dist[i][j] = double(fl32(sqrt(sum_k (x_i - x_j)^2))) from the summed table `sq` (in place
+// allowed); diagonal = `diag`.
+__device__ void finish_distances(const double* sq, int n, bool map_nonfinite, double diag, double* dist) {
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
     const int i = e / n, j = e - i * n;
     if (i < j) {
-      double v = (double)(float)sqrt(sum_parts(parts, nparts, (size_t)n * n, e));
+      double v = (double)(float)sqrt(sq[e]);
       if (map_nonfinite && !finite_d(v)) v = CUDART_INF;
       dist[i * n + j] = v;
-      dist[j * n + i] = v;
-    } else if (i == j) {
-      dist[e] = diag;
     }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e - i * n;
+    if (i > j) dist[e] = dist[j * n + i];
+    else if (i == j) dist[e] = diag;
   }
   __syncthreads();
 }
@@ -92,12 +115,14 @@ __device__ void stable_order(const double* key, int n, int32_t* __restrict__ ord
 // can only be reached after every finite distance, where the sum is +inf either way.
 __global__ void __launch_bounds__(kK5Threads)
 k5_score_select(const double* __restrict__ parts, int nparts, int n, int count, int32_t* __restrict__ order,
-                int32_t* __restrict__ status, int f, int m, int bulyan) {
+                int32_t* __restrict__ status, int f, int m, int bulyan, int slices) {
   extern __shared__ double sm[];
   double* dist = sm;
   double* sorted = sm + n * n;
   double* score = sm + 2 * n * n;
-  load_distances(parts, nparts, n, true, CUDART_INF, dist);
+  double* scratch = score + n;
+  block_sum_parts(parts, nparts, n * n, slices, scratch, dist);
+  finish_distances(dist, n, true, CUDART_INF, dist);
   sort_rows(dist, sorted, n);
   for (int i = threadIdx.x; i < n; i += blockDim.x) score[i] = py_sum(sorted + i * n, count);
   __syncthreads();
@@ -124,8 +149,10 @@ k5_score_select(const double* __restrict__ parts, int nparts, int n, int count, 
 __global__ void __launch_bounds__(256)
 k5_rowdist_select(const double* __restrict__ parts, int nparts, int n, int sqrt_norm, int32_t* __restrict__ order) {
   __shared__ double key[kMaxN];
+  __shared__ double scratch[4 * kMaxN];
+  block_sum_parts(parts, nparts, n, 4, scratch, key);
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const double s = sum_parts(parts, nparts, (size_t)n, i);
+    const double s = key[i];
     double v;
     if (sqrt_norm) {
       v = (double)(float)sqrt(s);
@@ -149,15 +176,17 @@ __device__ __forceinline__ unsigned long long sat_add(unsigned long long a, unsi
 
 __global__ void __launch_bounds__(kK5Threads)
 k5_brute_select(const double* __restrict__ parts, int nparts, int n, int f, unsigned long long total,
-                int32_t* __restrict__ sel, int32_t* __restrict__ status) {
+                int32_t* __restrict__ sel, int32_t* __restrict__ status, int slices) {
   extern __shared__ double sm[];
   double* dist = sm;                                                  // n*n
   unsigned long long* binom = reinterpret_cast<unsigned long long*>(sm + n * n);   // (n+1)*(n+1)
+  double* scratch = sm + n * n + (n + 1) * (n + 1);
   __shared__ double best_diam[kK5Threads / 32];
   __shared__ unsigned long long best_rank[kK5Threads / 32];
   const int k = n - f;
   const int W = n + 1;
-  load_distances(parts, nparts, n, false, 0., dist);
+  block_sum_parts(parts, nparts, n * n, slices, scratch, dist);
+  finish_distances(dist, n, false, 0., dist);
   // Pascal triangle, row by row
   for (int a = 0; a <= n; ++a) {
     for (int b = threadIdx.x; b <= n; b += blockDim.x) {
@@ -250,34 +279,44 @@ k5_brute_select(const double* __restrict__ parts, int nparts, int n, int f, unsi
 
 // ---- host side ---------------------------------------------------------------------------
 
-void launch_krum_select(const double* parts, int nparts, int n, int f, int32_t* order, cudaStream_t st) {
-  const size_t smem = (size_t)(2 * n * n + n) * sizeof(double);
-  static unsigned long long opted = 0;
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const unsigned long long bit = 1ull << (dev & 63);
-    if (!(opted & bit)) {
-      cudaFuncSetAttribute(k5_score_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2 * kMaxN * kMaxN + kMaxN) * sizeof(double)));
-      opted |= bit;
-    }
+// Interleaved part classes for block_sum_parts: as many as fit ~48 KB of scratch, at most 8.
+static int pick_slices(int n, int nparts) {
+  int slices = (int)((48 * 1024) / ((size_t)n * n * sizeof(double)));
+  if (slices > 8) slices = 8;
+  if (slices > nparts) slices = nparts;
+  if (slices < 1) slices = 1;
+  while (kK5Threads % slices) --slices;
+  return slices;
+}
+
+template <class K>
+static void opt_in_once(K kernel, size_t bytes, unsigned long long& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(mask & bit)) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    mask |= bit;
   }
-  k5_score_select<<<1, kK5Threads, smem, st>>>(parts, nparts, n, n - f - 1, order, nullptr, f, 0, 0);
+}
+
+constexpr size_t kScoreSmemMax = (size_t)(2 * kMaxN * kMaxN + kMaxN) * sizeof(double) + 48 * 1024;
+constexpr size_t kBruteSmemMax = (size_t)kMaxN * kMaxN * sizeof(double) + (size_t)(kMaxN + 1) * (kMaxN + 1) * sizeof(unsigned long long) + 48 * 1024;
+
+void launch_krum_select(const double* parts, int nparts, int n, int f, int32_t* order, cudaStream_t st) {
+  const int slices = pick_slices(n, nparts);
+  const size_t smem = (size_t)(2 * n * n + n + slices * n * n) * sizeof(double);
+  static unsigned long long opted = 0;
+  opt_in_once(k5_score_select, kScoreSmemMax, opted);
+  k5_score_select<<<1, kK5Threads, smem, st>>>(parts, nparts, n, n - f - 1, order, nullptr, f, 0, 0, slices);
 }
 
 void launch_bulyan_select(const double* parts, int nparts, int n, int f, int m, int32_t* order, int32_t* status, cudaStream_t st) {
-  const size_t smem = (size_t)(2 * n * n + n) * sizeof(double);
+  const int slices = pick_slices(n, nparts);
+  const size_t smem = (size_t)(2 * n * n + n + slices * n * n) * sizeof(double);
   static unsigned long long opted = 0;
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const unsigned long long bit = 1ull << (dev & 63);
-    if (!(opted & bit)) {
-      cudaFuncSetAttribute(k5_score_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2 * kMaxN * kMaxN + kMaxN) * sizeof(double)));
-      opted |= bit;
-    }
-  }
-  k5_score_select<<<1, kK5Threads, smem, st>>>(parts, nparts, n, m, order, status, f, m, 1);
+  opt_in_once(k5_score_select, kScoreSmemMax, opted);
+  k5_score_select<<<1, kK5Threads, smem, st>>>(parts, nparts, n, m, order, status, f, m, 1, slices);
 }
 
 int launch_brute_select(const double* parts, int nparts, int n, int f, int32_t* sel, int32_t* status, cudaStream_t st) {
@@ -290,19 +329,12 @@ int launch_brute_select(const double* parts, int nparts, int n, int f, int32_t* 
     total = total * num / i;
   }
   if (total > (1ull << 31)) return -1;
-  const size_t smem = (size_t)n * n * sizeof(double) + (size_t)(n + 1) * (n + 1) * sizeof(unsigned long long);
+  const int slices = pick_slices(n, nparts);
+  const size_t smem = (size_t)n * n * sizeof(double) + (size_t)(n + 1) * (n + 1) * sizeof(unsigned long long) +
+                      (size_t)slices * n * n * sizeof(double);
   static unsigned long long opted = 0;
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const unsigned long long bit = 1ull << (dev & 63);
-    if (!(opted & bit)) {
-      cudaFuncSetAttribute(k5_brute_select, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(kMaxN * kMaxN * sizeof(double) + (kMaxN + 1) * (kMaxN + 1) * sizeof(unsigned long long)));
-      opted |= bit;
-    }
-  }
-  k5_brute_select<<<1, kK5Threads, smem, st>>>(parts, nparts, n, f, total, sel, status);
+  opt_in_once(k5_brute_select, kBruteSmemMax, opted);
+  k5_brute_select<<<1, kK5Threads, smem, st>>>(parts, nparts, n, f, total, sel, status, slices);
   return 0;
 }
 

@@ -69,7 +69,7 @@ def test_median_trmean_every_n(n):
       amb = parity.closest_ambiguous(x.numpy(), n - f, center)
       parity.assert_close_scaled(got, ref, parity.column_scale(x.numpy()), f"{name} n={n} f={f}", exempt=amb)
 
-@pytest.mark.parametrize("n,f", [(11, 2), (11, 4), (11, 5), (25, 5), (25, 10), (25, 11), (51, 12), (51, 24)])
+@pytest.mark.parametrize("n,f", [(11, 1), (11, 2), (11, 4), (11, 5), (25, 1), (25, 5), (25, 7), (25, 10), (25, 11), (25, 12), (51, 1), (51, 12), (51, 17), (51, 24), (51, 25)])
 def test_trmean_specialised_pairs(n, f):
   """ The (n, f) pairs with a compile-time pruned network, incl. NaN / inf columns. """
   d = 4096 + 37
