@@ -214,7 +214,8 @@ def run_b200(args):
   dist = None
   if world > 1:
     import torch.distributed as dist
-    dist.init_process_group("nccl", device_id=device)
+    import datetime
+    dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=120))
   import byzantinemomentum_b200 as bz
   from byzantinemomentum_b200 import sharded
   bz._lib.lib()
@@ -244,11 +245,15 @@ def run_b200(args):
     total_ms, per_step = time_steps(torch, step, args.steps)
     barrier()
     # keep the sampler alive a little when the region is very short
+    # (a FIXED number of extra steps: every rank must issue the same collectives)
     if total_ms < 50:
-      t_end = time.perf_counter() + 0.05
-      k = 0
-      while time.perf_counter() < t_end:
-        step(k); k += 1
+      extra = int(min(2000, max(10, 50.0 / max(total_ms / args.steps, 1e-3))))
+      if dist is not None:
+        count = torch.tensor([extra], device=device, dtype=torch.int64)
+        dist.broadcast(count, src=0)
+        extra = int(count.item())
+      for k in range(extra):
+        step(k)
       torch.cuda.synchronize()
   if dist is not None:
     t = torch.tensor([total_ms], device=device, dtype=torch.float64)
