@@ -1,0 +1,98 @@
+# coding: utf-8
+"""GPU parity, part 3: the phases of the d-sharded path (A: partial distances, B: selection
+from gathered blocks, C: local reduce) composed by hand over R shards on ONE GPU must give the
+single-device result — what `byzantinemomentum_b200.sharded.aggregate` does across ranks with
+one all-gather in the middle."""
+
+import numpy as np
+import pytest
+
+import parity
+from oracle import byzoracle as orc
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+def _inputs(n, nb, d, seed):
+  gen = torch.Generator().manual_seed(seed)
+  mu = torch.randn(d, generator=gen)
+  honest = mu[None, :] + torch.linspace(0.5, 1.5, n - nb)[:, None] * torch.randn(n - nb, d, generator=gen)
+  byz = honest.mean(dim=0).mul(-1.1)
+  rows = [honest[i] for i in range(n - nb)] + [byz] * nb
+  return rows
+
+@pytest.mark.parametrize("n,nb,f,d,R", [(11, 3, 3, 4001, 2), (25, 5, 5, 10007, 4), (25, 5, 5, 10007, 8), (51, 12, 12, 3001, 3)])
+def test_phases_compose_to_the_single_device_result(n, nb, f, d, R):
+  from byzantinemomentum_b200 import engine
+  host = _inputs(n, nb, d, 77 + n)
+  np_rows = [r.numpy() for r in host]
+  full = [r.to(DEV) for r in host]
+  per = (d + R - 1) // R
+  shards = [[r[k * per:min(d, (k + 1) * per)] for r in full] for k in range(R)]    # unaligned views on purpose
+  def cat(outs):
+    return torch.cat(outs).cpu().numpy()
+  # krum
+  parts = torch.stack([engine.pairdist_partial(s) for s in shards])
+  order = engine.krum_select(parts, n, f)
+  ref, info = orc.krum(np_rows, f, return_info=True)
+  m = n - f - 2
+  assert [min(i, n - nb) for i in order.cpu().tolist()[:m]] == [min(i, n - nb) for i in info["selection"]]
+  parity.assert_bit_exact(cat([engine.average_selected(s, order, m) for s in shards]), ref, "krum sharded")
+  # same selection as the single-device call
+  out1, order1 = engine.krum(full, f, m)
+  assert order1.cpu().tolist()[:m] == order.cpu().tolist()[:m]
+  parity.assert_bit_exact(out1.cpu().numpy(), ref, "krum single")
+  # bulyan
+  if n >= 4 * f + 3:
+    order_b, status = engine.bulyan_select(parts, n, f, m)
+    assert int(status.item()) == 0
+    refb, infob = orc.bulyan(np_rows, f, return_info=True)
+    got = cat([engine.bulyan_reduce(s, f, m, order_b, status) for s in shards])
+    parity.assert_close_scaled(got, refb, parity.column_scale(infob["stage1"]), "bulyan sharded", exempt=infob["ambiguous"])
+  # brute (small n only)
+  if n <= 11:
+    sel, status = engine.brute_select(parts, n, f)
+    refr, infor = orc.brute(np_rows, f, return_info=True)
+    assert int(status.item()) == 0 and [min(i, n - nb) for i in sel.cpu().tolist()] == [min(i, n - nb) for i in infor["selection"]]
+    parity.assert_bit_exact(cat([engine.average_selected(s, sel, n - f, status=status) for s in shards]), refr, "brute sharded")
+  # cge
+  pn = torch.stack([engine.rowdist_partial(s) for s in shards])
+  order_c = engine.rowdist_select(pn, n, True)
+  refc = orc.cge(np_rows, f)
+  parity.assert_bit_exact(cat([engine.average_selected(s, order_c, n - f, zero_init=False) for s in shards]), refc, "cge sharded")
+  # aksel: the median is coordinate-local
+  meds = [engine.median(s) for s in shards]
+  pa = torch.stack([engine.rowdist_partial(s, c) for s, c in zip(shards, meds)])
+  order_a = engine.rowdist_select(pa, n, False)
+  refa, infoa = orc.aksel(np_rows, f, return_info=True)
+  c = (n + 1) // 2
+  assert [min(i, n - nb) for i in order_a.cpu().tolist()[:c]] == [min(i, n - nb) for i in infoa["selection"]]
+  parity.assert_bit_exact(cat([engine.average_selected(s, order_a, c) for s in shards]), refa, "aksel sharded")
+
+def test_sharded_aggregate_world_size_one():
+  """ `sharded.aggregate` without an initialised process group = one rank holding everything. """
+  from byzantinemomentum_b200 import sharded
+  n, nb, f, d = 11, 3, 3, 5003
+  host = _inputs(n, nb, d, 5)
+  np_rows = [r.numpy() for r in host]
+  rows = [r.to(DEV) for r in host]
+  for gar, params in (("median", {}), ("trmean", dict(f=f)), ("krum", dict(f=f)), ("brute", dict(f=f)), ("cge", dict(f=f)), ("aksel", dict(f=f))):
+    got = sharded.aggregate(gar, rows, **params).cpu().numpy()
+    parity.assert_bit_exact(got, orc.GARS[gar](np_rows, **params), gar)
+
+def test_plan_matches_plain_call_and_tracks_in_place_updates():
+  import byzantinemomentum_b200 as bz
+  n, f, d = 25, 10, 20003
+  x = torch.randn(n, d, generator=torch.Generator().manual_seed(9))
+  rows = [x[i].to(DEV) for i in range(n)]
+  plan = bz.Plan("trmean", rows, f=f)
+  parity.assert_bit_exact(plan().cpu().numpy(), orc.trmean([x[i].numpy() for i in range(n)], f), "plan")
+  rows[3].mul_(-2.5)          # momentum buffers are updated in place between steps
+  x[3].mul_(-2.5)
+  parity.assert_bit_exact(plan().cpu().numpy(), orc.trmean([x[i].numpy() for i in range(n)], f), "plan after update")
+  kp = bz.Plan("krum", rows, f=5)
+  out = kp().cpu().numpy()
+  ref, info = orc.krum([x[i].numpy() for i in range(n)], 5, return_info=True)
+  assert kp.selection.cpu().tolist()[:n - 7] == info["selection"]
+  parity.assert_bit_exact(out, ref, "krum plan")
