@@ -82,8 +82,10 @@ int run_sorted(const float* const* rows, int n, int mode, int f, int64_t d, floa
   RowTable t;
   fill_table(t, rows, n);
   const Geom g = make_geom(rows, n, out, nullptr, d, body_vec(n));
-  if (!(mode == kModeTrmean && launch_trmean_special(n, f, t, g, out, st)))
-    launch_sorted(n, t, g, mode, f, out, st);
+  const bool special = (mode == kModeTrmean) ? launch_trmean_special(n, f, t, g, out, st)
+                     : (mode == kModePhocas) ? launch_phocas_special(n, f, t, g, out, st)
+                                             : launch_meamed_special(n, f, t, g, out, st);
+  if (!special) launch_sorted(n, t, g, mode, f, out, st);
   return check_launch("k1_sorted");
 }
 

@@ -48,4 +48,8 @@ void launch_rowdist_select(const double* parts, int nparts, int n, int sqrt_norm
 bool launch_bulyan_reduce(const RowTable& rows, int n, int f, int m, const int32_t* order, const int32_t* status,
                           int64_t d, float* out, cudaStream_t st);
 
+// (n, f) with a compile-time specialisation and the default m; false otherwise.
+bool launch_bulyan_reduce_static(const RowTable& rows, int n, int f, int m, const int32_t* order, const int32_t* status,
+                                 const Geom& g, float* out, cudaStream_t st);
+
 }  // namespace bz

@@ -1,11 +1,11 @@
 // k1_inst.cu — instantiations of the K1 kernels for a range of n, compiled once per part
-// (`-DBZ_PART=<0..8>`) so that the kernels build in parallel.  Parts 0-3: k1_median for n in
-// 1-16 / 17-32 / 33-48 / 49-64; parts 4-7: generic k1_sorted for the same ranges; part 8:
-// trimmed mean with (n, f) fixed at compile time for the reference's experiment grids.
+// (`-DBZ_PART=<0..10>`) so that the kernels build in parallel.  Parts 0-3: k1_median for n in
+// 1-16 / 17-32 / 33-48 / 49-64; parts 4-7: generic k1_sorted for the same ranges; parts 8-10:
+// trimmed mean / phocas / meamed with (n, f) fixed at compile time for n = 11, 25, 51.
 #include "k1_select.cuh"
 
 #ifndef BZ_PART
-#error "compile with -DBZ_PART=<0..8>"
+#error "compile with -DBZ_PART=<0..10>"
 #endif
 
 #if (BZ_PART % 4) == 0
@@ -111,17 +111,28 @@ bool BZ_FN(BZ_PART)(int n, const RowTable& rows, const Geom& g, int mode, int f,
   Y(51, 1) Y(51, 2) Y(51, 3) Y(51, 4) Y(51, 5) Y(51, 6) Y(51, 7) Y(51, 8) Y(51, 9) Y(51, 10) Y(51, 11) Y(51, 12) Y(51, 13) \
   Y(51, 14) Y(51, 15) Y(51, 16) Y(51, 17) Y(51, 18) Y(51, 19) Y(51, 20) Y(51, 21) Y(51, 22) Y(51, 23) Y(51, 24) Y(51, 25)
 
+#if BZ_PART == 8
+#define BZ_SPECIAL_MODE kModeTrmean
+#define BZ_SPECIAL_FN launch_trmean_special
+#elif BZ_PART == 9
+#define BZ_SPECIAL_MODE kModePhocas
+#define BZ_SPECIAL_FN launch_phocas_special
+#else
+#define BZ_SPECIAL_MODE kModeMeamed
+#define BZ_SPECIAL_FN launch_meamed_special
+#endif
+
 template <int N, int F>
-static void launch_trmean_nf(const RowTable& rows, const Geom& g, float* out, cudaStream_t st) {
+static void launch_special_nf(const RowTable& rows, const Geom& g, float* out, cudaStream_t st) {
   if (g.nv <= 0) return;
   static int cache[64] = {0};
   const size_t smem = Stage<N, body_vec(N)>::kFloats * sizeof(float);
-  k1_sorted<N, body_vec(N), F, kModeTrmean><<<persistent_grid(k1_sorted<N, body_vec(N), F, kModeTrmean>, smem, g.nv, cache), kK1Threads, smem, st>>>(rows, g, kModeTrmean, F, out);
+  k1_sorted<N, body_vec(N), F, BZ_SPECIAL_MODE><<<persistent_grid(k1_sorted<N, body_vec(N), F, BZ_SPECIAL_MODE>, smem, g.nv, cache), kK1Threads, smem, st>>>(rows, g, BZ_SPECIAL_MODE, F, out);
 }
 
-bool launch_trmean_special(int n, int f, const RowTable& rows, const Geom& g, float* out, cudaStream_t st) {
+bool BZ_SPECIAL_FN(int n, int f, const RowTable& rows, const Geom& g, float* out, cudaStream_t st) {
   if (g.vec == 1) return false;   // unaligned rows take the generic scalar kernel
-#define Y(N, F) if (n == N && f == F) { launch_trmean_nf<N, F>(rows, g, out, st); return true; }
+#define Y(N, F) if (n == N && f == F) { launch_special_nf<N, F>(rows, g, out, st); return true; }
   BZ_NF_LIST
 #undef Y
   return false;

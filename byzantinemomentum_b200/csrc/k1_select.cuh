@@ -169,6 +169,22 @@ __device__ __forceinline__ float closest_pairs(const float (&s)[N], int m, float
   return (c != c) ? quiet_nan() : r;
 }
 
+// Compile-time f: the partner index l + m is a literal, no staging needed.
+template <int N, int F>
+__device__ __forceinline__ float closest_pairs_static(const float (&s)[N], float c) {
+  constexpr int M = N - F;
+  float acc = 0.f;
+#pragma unroll
+  for (int l = 0; l < F; ++l) {
+    const int dlo = abs_key(__fsub_rn(s[l], c)), dhi = abs_key(__fsub_rn(s[l + M], c));
+    acc = __fadd_rn(acc, (dlo > dhi) ? s[l + M] : s[l]);
+  }
+#pragma unroll
+  for (int k = F; k < M; ++k) acc = __fadd_rn(acc, s[k]);
+  const float r = __fdiv_rn(acc, (float)M);
+  return (c != c) ? quiet_nan() : r;
+}
+
 template <int N, int VEC, int F, int MODE>
 __global__ void __launch_bounds__(kK1Threads)
 k1_sorted(const __grid_constant__ RowTable rows, const Geom g, const int mode_rt, const int f_rt,
@@ -218,7 +234,8 @@ k1_sorted(const __grid_constant__ RowTable rows, const Geom g, const int mode_rt
             // lower median; NaN sorts last, so a NaN anywhere shows in the last rank (median.py:39)
             center = (x[c][N - 1] != x[c][N - 1]) ? quiet_nan() : x[c][(N - 1) / 2];
           }
-          res[c] = closest_pairs<N>(x[c], N - f, center, sorted_cols + c * kK1Threads + threadIdx.x, VEC * kK1Threads);
+          if (F >= 0) res[c] = closest_pairs_static<N, (F >= 0 ? F : 0)>(x[c], center);
+          else        res[c] = closest_pairs<N>(x[c], N - f, center, sorted_cols + c * kK1Threads + threadIdx.x, VEC * kK1Threads);
         }
       }
     }

@@ -16,6 +16,8 @@
 // Every pair walks the coordinates in the same lane/step pattern, so identical data (aliased
 // rows) give bitwise identical sums.
 // Roofline: HBM n·4 B per coordinate; secondary: FP32 pipe, n(n-1) lane-ops per coordinate.
+#include <cstdlib>
+
 #include "dist.cuh"
 #include "reduce.cuh"
 
@@ -190,14 +192,172 @@ k2_pairdist(const __grid_constant__ RowTable rows, const int n, const int T, con
   }
 }
 
+// ---- K2 with TMA staging -------------------------------------------------------------------
+// Same task layout and arithmetic as k2_pairdist, but full tiles are brought in by the TMA
+// engine: ONE thread issues n bulk copies (cp.async.bulk, T·4 bytes each) per tile into a ring
+// of kStages shared-memory stages, completion is signalled on an mbarrier (`full`), consumers
+// release a stage through a second mbarrier (`empty`).  No block-wide barrier in the steady
+// state and none of the per-thread address arithmetic of the cp.async loop (which cost ~25 %
+// of the issue slots).  Needs 16-byte aligned rows; the ragged tail tile (and unaligned rows)
+// take the cooperative path.  The producer is lane 0 of warp 0, whose own task is a diagonal
+// (light) one, so waiting for the slowest warp before re-arming a stage costs it nothing.
+constexpr int kTmaT = 512;          // coordinates per tile
+constexpr int kTmaLogQ = 7;         // log2(kTmaT / 4)
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(float* dst, const float* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(kK2Threads, 1)
+k2_pairdist_tma(const __grid_constant__ RowTable rows, const int n, const int64_t d, const int64_t nfull,
+                double* __restrict__ parts) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int T = kTmaT;
+  float* stages = reinterpret_cast<float*>(smem_raw);
+  const int stage_floats = n * T;
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)STAGES * stage_floats * sizeof(float));
+  unsigned long long* empty = full + STAGES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ng = (n + kG - 1) / kG;
+  const int ntasks = ng * (ng + 1) / 2;
+  const int task = blockIdx.y * kK2Warps + warp;
+  const bool active = task < ntasks;
+  const int nactive = min(kK2Warps, ntasks - (int)blockIdx.y * kK2Warps);
+  int ga = 0, gb = 0;
+  if (active) {
+    int t = task;
+    while (t >= ng - ga) { t -= ng - ga; ++ga; }
+    gb = ga + t;
+  }
+  const bool diag = ga == gb;
+  int oa[kG], ob[kG];
+#pragma unroll
+  for (int i = 0; i < kG; ++i) {
+    oa[i] = min(ga * kG + i, n - 1) * T;
+    ob[i] = min(gb * kG + i, n - 1) * T;
+  }
+  u64 acc[kG * kG];
+#pragma unroll
+  for (int p = 0; p < kG * kG; ++p) acc[p] = 0ull;
+  double dacc = 0.;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nactive); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // Full tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ... < nfull
+  const int64_t mine = (nfull > (int64_t)blockIdx.x) ? (nfull - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const unsigned tile_bytes = (unsigned)(n * T * sizeof(float));
+  auto issue = [&](int64_t k) {      // producer thread only
+    const int s = (int)(k % STAGES);
+    float* dst = stages + (size_t)s * stage_floats;
+    const int64_t base = (blockIdx.x + k * gridDim.x) * (int64_t)T;
+    mbar_expect_tx(&full[s], tile_bytes);
+    for (int r = 0; r < n; ++r) tma_load_1d(dst + r * T, rows.p[r] + base, T * sizeof(float), &full[s]);
+  };
+  if (threadIdx.x == 0)
+    for (int64_t k = 0; k < mine && k < STAGES; ++k) issue(k);
+
+  int pending = 0;
+  for (int64_t k = 0; k < mine; ++k) {
+    const int s = (int)(k % STAGES);
+    const unsigned parity = (unsigned)((k / STAGES) & 1);
+    if (active) {
+      mbar_wait(&full[s], parity);
+      const float* buf = stages + (size_t)s * stage_floats;
+      if (diag) sweep_tile<true>(buf, T, oa, ob, lane, acc);
+      else      sweep_tile<false>(buf, T, oa, ob, lane, acc);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      if (++pending == 2) {          // <= 16 terms per accumulator half between flushes
+        pending = 0;
+        if (diag) flush<10>(acc, lane, dacc); else flush<kG * kG>(acc, lane, dacc);
+      }
+    }
+    if (threadIdx.x == 0 && k + STAGES < mine) {
+      mbar_wait(&empty[s], parity);  // every consumer warp has released the stage
+      issue(k + STAGES);
+    }
+  }
+  // Ragged tail tile (d not a multiple of T): cooperative staging with zero fill, one CTA
+  const int64_t ntiles = (d + T - 1) / T;
+  if (ntiles > nfull && (nfull % gridDim.x) == blockIdx.x) {
+    __syncthreads();                 // the ring is drained: stage 0 is free
+    stage_tile(stages, rows, n, T, kTmaLogQ, nfull * T, d);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    if (active) {
+      if (diag) sweep_tile<true>(stages, T, oa, ob, lane, acc);
+      else      sweep_tile<false>(stages, T, oa, ob, lane, acc);
+      pending = 1;
+    }
+  }
+  if (active && pending > 0) {
+    if (diag) flush<10>(acc, lane, dacc); else flush<kG * kG>(acc, lane, dacc);
+  }
+  if (active) {
+    int i, j;
+    bool valid;
+    if (diag) {
+      i = (lane >= 9) ? 3 : (lane >= 7) ? 2 : (lane >= 4) ? 1 : 0;
+      const int first = (i == 0) ? 0 : (i == 1) ? 4 : (i == 2) ? 7 : 9;
+      j = lane - first + i + 1;
+      valid = lane < 10;
+    } else {
+      i = lane / kG; j = lane % kG;
+      valid = lane < kG * kG;
+    }
+    const int ri = ga * kG + i, rj = gb * kG + j;
+    if (valid && ri < n && rj < n) parts[(size_t)blockIdx.x * n * n + (size_t)ri * n + rj] = dacc;
+  }
+}
+
 // ---- fixed-order reduction of partial blocks --------------------------------------------------
-__global__ void k_reduce_parts(const double* __restrict__ parts, int nparts, int len, int pair_n, double* __restrict__ block) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= len) return;
-  if (pair_n > 0 && (e / pair_n) >= (e % pair_n)) { block[e] = 0.; return; }
+// One CTA per 32 entries; warp w adds the blocks p = w, w + 8, ... (coalesced 256-byte rows of
+// 32 entries), the 8 warp sums are then added in warp order: a fixed order, whatever the grid.
+constexpr int kReduceWarps = 8;
+__global__ void __launch_bounds__(kReduceWarps * 32)
+k_reduce_parts(const double* __restrict__ parts, int nparts, int len, int pair_n, double* __restrict__ block) {
+  __shared__ double partial[kReduceWarps][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * 32 + lane;
   double s = 0.;
-  for (int p = 0; p < nparts; ++p) s += parts[(size_t)p * len + e];
-  block[e] = s;
+  if (e < len)
+    for (int p = warp; p < nparts; p += kReduceWarps) s += parts[(size_t)p * len + e];
+  partial[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && e < len) {
+    double total = 0.;
+#pragma unroll
+    for (int w = 0; w < kReduceWarps; ++w) total += partial[w][lane];
+    if (pair_n > 0 && (e / pair_n) >= (e % pair_n)) total = 0.;
+    block[e] = total;
+  }
 }
 
 // ---- host side ---------------------------------------------------------------------------
@@ -211,8 +371,45 @@ static int sm_count() {
   return c > 0 ? c : 148;
 }
 
+template <int STAGES>
+static void launch_tma(const RowTable& rows, int n, int64_t d, int gx, int gy, double* parts, cudaStream_t st) {
+  const size_t smem = (size_t)STAGES * n * kTmaT * sizeof(float) + 2 * STAGES * sizeof(unsigned long long);
+  static unsigned long long opted = 0;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(opted & bit)) {
+      cudaFuncSetAttribute(k2_pairdist_tma<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK2SmemBudget);
+      opted |= bit;
+    }
+  }
+  k2_pairdist_tma<STAGES><<<dim3(gx, gy), kK2Threads, smem, st>>>(rows, n, d, d / kTmaT, parts);
+}
+
 int launch_pairdist(const RowTable& rows, int n, int64_t d, double* parts, cudaStream_t st) {
-  // Largest power-of-two tile whose two stages fit the shared memory of one CTA per SM
+  const int ng = (n + kG - 1) / kG;
+  const int ntasks = ng * (ng + 1) / 2;
+  const int gy = (ntasks + kK2Warps - 1) / kK2Warps;
+  // TMA path: every row 16-byte aligned and at least 3 ring stages of n x 512 floats fit
+  bool aligned = true;
+  for (int r = 0; r < n && aligned; ++r) aligned = (((uintptr_t)rows.p[r]) & 15) == 0;
+  const size_t stage_bytes = (size_t)n * kTmaT * sizeof(float);
+  const int stages_fit = (int)((kK2SmemBudget - 256) / stage_bytes);
+  static const bool force_generic = getenv("BYZAGG_K2_GENERIC") != nullptr;
+  if (aligned && stages_fit >= 3 && !force_generic) {   // with 2 stages the cp.async path measured faster (n > 36)
+    const int64_t ntiles = (d + kTmaT - 1) / kTmaT;
+    int gx = sm_count() / (gy > 0 ? gy : 1);
+    if (gx < 1) gx = 1;
+    if (gx > kMaxParts) gx = kMaxParts;
+    if ((int64_t)gx > ntiles) gx = (int)(ntiles > 0 ? ntiles : 1);
+    if (stages_fit >= 4)      launch_tma<4>(rows, n, d, gx, gy, parts, st);
+    else if (stages_fit == 3) launch_tma<3>(rows, n, d, gx, gy, parts, st);
+    else                      launch_tma<2>(rows, n, d, gx, gy, parts, st);
+    return gx;
+  }
+  // Generic path: cp.async staging, any alignment.  Largest power-of-two tile whose two stages
+  // fit the shared memory of one CTA per SM
   int T = 1024;
   while (T > 128 && (size_t)2 * n * T * sizeof(float) > kK2SmemBudget) T >>= 1;
   int logq = 0;
@@ -228,9 +425,6 @@ int launch_pairdist(const RowTable& rows, int n, int64_t d, double* parts, cudaS
       opted |= bit;
     }
   }
-  const int ng = (n + kG - 1) / kG;
-  const int ntasks = ng * (ng + 1) / 2;
-  const int gy = (ntasks + kK2Warps - 1) / kK2Warps;
   const int64_t ntiles = (d + T - 1) / T;
   int gx = sm_count() / (gy > 0 ? gy : 1);
   if (gx < 1) gx = 1;
@@ -241,7 +435,7 @@ int launch_pairdist(const RowTable& rows, int n, int64_t d, double* parts, cudaS
 }
 
 void launch_reduce_parts(const double* parts, int nparts, int len, int pair_n, double* block, cudaStream_t st) {
-  k_reduce_parts<<<(len + 255) / 256, 256, 0, st>>>(parts, nparts, len, pair_n, block);
+  k_reduce_parts<<<(len + 31) / 32, kReduceWarps * 32, 0, st>>>(parts, nparts, len, pair_n, block);
 }
 
 }  // namespace bz

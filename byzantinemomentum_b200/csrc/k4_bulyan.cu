@@ -72,6 +72,97 @@ k4_bulyan(const __grid_constant__ RowTable rows, const int64_t d, const int n, c
   out[e] = (med != med) ? quiet_nan() : r;
 }
 
+// ---- compile-time (n, f), default m = n-f-2: everything in registers ------------------------
+// For the (n, f) of BASELINE.json's configs and of the reference's grids.  The m_max rows of a
+// coordinate are m_max literal registers (all loads in flight at once), the theta running
+// means are fully unrolled chains, the closest-beta window needs no shared memory because
+// theta and beta are literals (only the window start is run-time: predicated adds).
+template <int N, int F, int VEC>
+__global__ void __launch_bounds__(kK4Threads)
+k4_bulyan_static(const __grid_constant__ RowTable rows, const Geom g, const int32_t* __restrict__ order,
+                 const int32_t* __restrict__ status, float* __restrict__ out) {
+  constexpr int M_MAX = N - F - 2, THETA = N - 2 * F - 2, BETA = THETA - 2 * F, R = THETA - BETA;
+  const int64_t v = (int64_t)blockIdx.x * kK4Threads + threadIdx.x;
+  if (v >= g.nv) return;
+  const int64_t e0 = v * VEC - g.shift;
+  const bool full = e0 >= 0 && e0 + VEC <= g.d;
+  float res[VEC];
+  if (status != nullptr && *status != 0) {
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) res[c] = quiet_nan();
+    store_vec<VEC>(out, e0, g.d, full, res);
+    return;
+  }
+  float x[VEC][M_MAX];
+  if (full) {
+#pragma unroll
+    for (int k = 0; k < M_MAX; ++k) {
+      float t[VEC];
+      VecLoad<VEC>::load(rows.p[order[k]] + e0, t);
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) x[c][k] = t[c];
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < M_MAX; ++k)
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) {
+        const int64_t e = e0 + c;
+        x[c][k] = (e >= 0 && e < g.d) ? __ldcs(rows.p[order[k]] + e) : 0.f;
+      }
+  }
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) {
+    // Stage 1 (bulyan.py:66-70, scores never updated): selected[i] = (0 + v[i] + ... + v[M_MAX-1]) / (M_MAX - i)
+    int key[THETA];
+#pragma unroll
+    for (int it = 0; it < THETA; ++it) {
+      float acc = __fadd_rn(0.f, x[c][it]);
+#pragma unroll
+      for (int q = it + 1; q < M_MAX; ++q) acc = __fadd_rn(acc, x[c][q]);
+      key[it] = float_to_key(__fdiv_rn(acc, (float)(M_MAX - it)));
+    }
+    // Stage 2 (bulyan.py:78-84)
+    SortNet<THETA>::template run<OpsKey>(key);
+    float s[THETA];
+#pragma unroll
+    for (int it = 0; it < THETA; ++it) s[it] = key_to_float(key[it]);
+    const float med = (s[THETA - 1] != s[THETA - 1]) ? quiet_nan() : s[(THETA - 1) / 2];
+    int lstar = 0;
+#pragma unroll
+    for (int l = 0; l < R; ++l) {
+      const int dlo = abs_key(__fsub_rn(s[l], med)), dhi = abs_key(__fsub_rn(s[l + BETA], med));
+      lstar = (dlo > dhi) ? l + 1 : lstar;
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < THETA; ++k) {
+      const bool in = (unsigned)(k - lstar) < (unsigned)BETA;
+      acc = in ? __fadd_rn(acc, s[k]) : acc;
+    }
+    const float r = __fdiv_rn(acc, (float)BETA);
+    res[c] = (med != med) ? quiet_nan() : r;
+  }
+  store_vec<VEC>(out, e0, g.d, full, res);
+}
+
+template <int N, int F>
+static void launch_static(const RowTable& rows, const Geom& g, const int32_t* order, const int32_t* status, float* out, cudaStream_t st) {
+  if (g.nv <= 0) return;
+  const unsigned blocks = (unsigned)((g.nv + kK4Threads - 1) / kK4Threads);
+  if (g.vec == 2) k4_bulyan_static<N, F, 2><<<blocks, kK4Threads, 0, st>>>(rows, g, order, status, out);
+  else            k4_bulyan_static<N, F, 1><<<blocks, kK4Threads, 0, st>>>(rows, g, order, status, out);
+}
+
+bool launch_bulyan_reduce_static(const RowTable& rows, int n, int f, int m, const int32_t* order, const int32_t* status,
+                                 const Geom& g, float* out, cudaStream_t st) {
+  if (m != n - f - 2) return false;
+#define Y(N, F) if (n == N && f == F) { launch_static<N, F>(rows, g, order, status, out, st); return true; }
+  Y(11, 2) Y(25, 5) Y(51, 12)
+#undef Y
+  return false;
+}
+
 template <int THETA>
 static void launch_theta(const RowTable& rows, int64_t d, int n, int f, int m, const int32_t* order,
                          const int32_t* status, float* out, cudaStream_t st) {

@@ -26,11 +26,26 @@ __device__ void block_sum_parts(const double* __restrict__ parts, int nparts, in
                                 double* __restrict__ scratch, double* __restrict__ out) {
   const int T = blockDim.x / slices;            // threads per slice
   const int slice = threadIdx.x / T, t = threadIdx.x - slice * T;
+  constexpr int E = 8;                          // entries per thread in flight together
   if (slice < slices) {
-    for (int e = t; e < len; e += T) {
-      double s = 0.;
-      for (int p = slice; p < nparts; p += slices) s += parts[(size_t)p * len + e];
-      scratch[slice * len + e] = s;
+    for (int e0 = t; e0 < len; e0 += T * E) {
+      double s[E];
+#pragma unroll
+      for (int q = 0; q < E; ++q) s[q] = 0.;
+#pragma unroll 4
+      for (int p = slice; p < nparts; p += slices) {
+        const double* __restrict__ row = parts + (size_t)p * len;
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+          const int e = e0 + q * T;
+          if (e < len) s[q] += row[e];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < E; ++q) {
+        const int e = e0 + q * T;
+        if (e < len) scratch[slice * len + e] = s[q];
+      }
     }
   }
   __syncthreads();
@@ -146,11 +161,12 @@ k5_score_select(const double* __restrict__ parts, int nparts, int n, int count, 
 }
 
 // aksel.py:39-49 / cge.py:28-38: stable order of n keys.
-__global__ void __launch_bounds__(256)
+constexpr int kRowSelThreads = 1024, kRowSelSlices = 16;   // 64 threads per slice: one per row
+__global__ void __launch_bounds__(kRowSelThreads)
 k5_rowdist_select(const double* __restrict__ parts, int nparts, int n, int sqrt_norm, int32_t* __restrict__ order) {
   __shared__ double key[kMaxN];
-  __shared__ double scratch[4 * kMaxN];
-  block_sum_parts(parts, nparts, n, 4, scratch, key);
+  __shared__ double scratch[kRowSelSlices * kMaxN];
+  block_sum_parts(parts, nparts, n, kRowSelSlices, scratch, key);
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double s = key[i];
     double v;
@@ -339,7 +355,7 @@ int launch_brute_select(const double* parts, int nparts, int n, int f, int32_t* 
 }
 
 void launch_rowdist_select(const double* parts, int nparts, int n, int sqrt_norm, int32_t* order, cudaStream_t st) {
-  k5_rowdist_select<<<1, 256, 0, st>>>(parts, nparts, n, sqrt_norm, order);
+  k5_rowdist_select<<<1, kRowSelThreads, 0, st>>>(parts, nparts, n, sqrt_norm, order);
 }
 
 }  // namespace bz

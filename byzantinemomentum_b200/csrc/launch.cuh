@@ -25,6 +25,8 @@ bool launch_sorted_part5(int n, const RowTable& rows, const Geom& g, int mode, i
 bool launch_sorted_part6(int n, const RowTable& rows, const Geom& g, int mode, int f, float* out, cudaStream_t st);
 bool launch_sorted_part7(int n, const RowTable& rows, const Geom& g, int mode, int f, float* out, cudaStream_t st);
 bool launch_trmean_special(int n, int f, const RowTable& rows, const Geom& g, float* out, cudaStream_t st);
+bool launch_phocas_special(int n, int f, const RowTable& rows, const Geom& g, float* out, cudaStream_t st);
+bool launch_meamed_special(int n, int f, const RowTable& rows, const Geom& g, float* out, cudaStream_t st);
 
 // K3 (k3_average.cu): ordered-subset average.
 void launch_average(const RowTable& rows, const Geom& g, const int32_t* sel, int count,

@@ -76,30 +76,43 @@ def _validate(gradients):
     contiguous = contiguous and grad.is_contiguous()
   return first, contiguous
 
-class _LastCall:
-  """ One-entry cache of the prepared arguments of the last call on CUDA tensors, keyed by the
-  identity of the tensor objects (held through weak references) and re-validated against their
-  current data pointers: a trainer that aggregates the same momentum buffers every step
-  (attack.py:800-804) pays for the list validation once. """
-  __slots__ = ("ids", "refs", "addresses", "prep")
+class _CallCache:
+  """ Small cache of prepared arguments for calls on CUDA tensors, keyed by the identity of the
+  tensor objects (held through weak references) and re-validated against their current data
+  pointers: a trainer that aggregates the same momentum buffers every step (attack.py:800-804)
+  pays for the list validation once.  At most `capacity` lists, oldest evicted first. """
+  capacity = 8
   def __init__(self):
-    self.ids = self.refs = self.addresses = self.prep = None
+    self.entries = {}          # ids tuple -> (refs, addresses, prep)
+  def lookup(self, gradients):
+    if not self.entries or type(gradients) is not list:
+      return None
+    entry = self.entries.get(tuple(map(id, gradients)))
+    if entry is None:
+      return None
+    refs, addresses, prep = entry
+    for ref, grad in zip(refs, gradients):
+      if ref() is not grad:
+        return None
+    if tuple([g.data_ptr() for g in gradients]) != addresses or gradients[0].numel() != prep.d:
+      return None
+    return prep
+  def store(self, gradients, addresses, prep):
+    try:
+      refs = [weakref.ref(g) for g in gradients]
+    except TypeError:
+      return
+    if len(self.entries) >= self.capacity:
+      self.entries.pop(next(iter(self.entries)))
+    self.entries[tuple(map(id, gradients))] = (refs, addresses, prep)
 
-_last_call = _LastCall()
+_call_cache = _CallCache()
 
 def _prepare(gradients):
-  cache = _last_call
-  if cache.ids is not None and type(gradients) is list and len(gradients) == cache.prep.n:
-    if tuple(map(id, gradients)) == cache.ids:
-      alive = True
-      for ref, grad in zip(cache.refs, gradients):
-        if ref() is not grad:
-          alive = False
-          break
-      if alive and tuple([g.data_ptr() for g in gradients]) == cache.addresses and gradients[0].numel() == cache.prep.d:
-        prep = cache.prep
-        prep.stream = torch.cuda.current_stream(prep.device).cuda_stream
-        return prep
+  prep = _call_cache.lookup(gradients)
+  if prep is not None:
+    prep.stream = torch.cuda.current_stream(prep.device).cuda_stream
+    return prep
   first, contiguous = _validate(gradients)
   if not torch.cuda.is_available():
     raise _lib.LibraryError("no CUDA device available: byzantinemomentum_b200 runs on B200 GPUs only (no CPU fallback)")
@@ -139,14 +152,8 @@ def _prepare(gradients):
   prep.ptrs = (ctypes.c_void_p * n)(*addresses)
   prep.stream = torch.cuda.current_stream(device).cuda_stream
   if not prep.to_cpu and contiguous and type(gradients) is list:
-    try:
-      cache.refs = [weakref.ref(g) for g in gradients]
-      cache.ids = tuple(map(id, gradients))
-      cache.addresses = addresses
-      prep.rows = None          # the cache must not keep the gradients alive
-      cache.prep = prep
-    except TypeError:
-      cache.ids = None
+    prep.rows = None            # the cache must not keep the gradients alive
+    _call_cache.store(gradients, addresses, prep)
   return prep
 
 class _on:
