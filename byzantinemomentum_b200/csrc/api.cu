@@ -27,7 +27,7 @@ int check_launch(const char* what) {
 }
 
 Geom make_geom(const float* const* rows, int n, const void* out, const void* extra, int64_t d, int want_vec) {
-  Geom g{d, d, 0, 1};
+  Geom g{d, d, 0, 1, 1, -1};
   if (want_vec <= 1 || d < 1) return g;
   const uintptr_t bytes = (uintptr_t)want_vec * sizeof(float);
   const uintptr_t mis = (uintptr_t)rows[0] % bytes;

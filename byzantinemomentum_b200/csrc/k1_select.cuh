@@ -111,11 +111,26 @@ __global__ void __launch_bounds__(kK1Threads)
 k1_median(const __grid_constant__ RowTable rows, const Geom g, float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
   k1_walk<N, VEC>(rows, g, smem, [&](float (&x)[VEC][N], int64_t e0, bool full) {
-    float res[VEC];
+    float chk = 0.f;
 #pragma unroll
-    for (int c = 0; c < VEC; ++c) {
-      SortNet<N>::template run<OpsNaNProp>(x[c]);
-      res[c] = x[c][(N - 1) / 2];   // lower median; every other output is dead code
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) chk = fmaf(x[c][r], 0.f, chk);   // NaN iff a NaN / inf is present
+    float res[VEC];
+    if (chk == chk) {
+      // all finite: comparators split over the ALU and FMA pipes
+      const OpsMix<MixMedian<N>> ops{g.one, g.mone};
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) {
+        SortNet<N>::run(ops, x[c]);
+        res[c] = x[c][(N - 1) / 2];   // lower median; every other output is dead code
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) {
+        SortNet<N>::run(OpsNaNProp{}, x[c]);
+        res[c] = x[c][(N - 1) / 2];
+      }
     }
     store_vec<VEC>(out, e0, g.d, full, res);
   });
@@ -185,6 +200,10 @@ __device__ __forceinline__ float closest_pairs_static(const float (&s)[N], float
   return (c != c) ? quiet_nan() : r;
 }
 
+// Mask of the mixed comparators: pruned for a compile-time trimmed mean, full sort otherwise.
+template <int N, int F, int MODE> struct MixFor { typedef OpsMix<MixFull<N>> type; };
+template <int N, int F> struct MixFor<N, F, kModeTrmean> { typedef OpsMix<MixTrim<N, F>> type; };
+
 template <int N, int VEC, int F, int MODE>
 __global__ void __launch_bounds__(kK1Threads)
 k1_sorted(const __grid_constant__ RowTable rows, const Geom g, const int mode_rt, const int f_rt,
@@ -202,10 +221,12 @@ k1_sorted(const __grid_constant__ RowTable rows, const Geom g, const int mode_rt
         chk = fmaf(x[c][r], 0.f, chk);   // NaN iff some value is NaN or +-inf (FMA pipe, off the ALU pipe)
     float res[VEC];
     if (chk == chk) {
-      // Fast path: all finite, plain FMNMX network
+      // Fast path: all finite, FMNMX / IMAD network (for a compile-time trimmed mean the mask is
+      // the one balanced for the ranks it reads)
+      const typename MixFor<N, F, MODE>::type ops{g.one, g.mone};
 #pragma unroll
       for (int c = 0; c < VEC; ++c) {
-        SortNet<N>::template run<OpsFast>(x[c]);
+        SortNet<N>::run(ops, x[c]);
         if (MODE == kModeTrmean) res[c] = trmean_sorted<N>(x[c], f);
       }
     } else {
@@ -215,7 +236,7 @@ k1_sorted(const __grid_constant__ RowTable rows, const Geom g, const int mode_rt
         int k[N];
 #pragma unroll
         for (int r = 0; r < N; ++r) k[r] = float_to_key(x[c][r]);
-        SortNet<N>::template run<OpsKey>(k);
+        SortNet<N>::run(OpsKey{}, k);
 #pragma unroll
         for (int r = 0; r < N; ++r) x[c][r] = key_to_float(k[r]);
         if (MODE == kModeTrmean) res[c] = trmean_sorted<N>(x[c], f);

@@ -48,7 +48,7 @@ k4_bulyan(const __grid_constant__ RowTable rows, const int64_t d, const int n, c
     key[it] = float_to_key(__fdiv_rn(acc, (float)mi));
   }
   // Stage 2 (bulyan.py:78-84): lower median over theta, beta closest to it, mean
-  SortNet<THETA>::template run<OpsKey>(key);
+  SortNet<THETA>::run(OpsKey{}, key);
   float last = key_to_float(key[THETA - 1]);
   const float med = (last != last) ? quiet_nan() : key_to_float(key[(THETA - 1) / 2]);
 #pragma unroll
@@ -123,7 +123,7 @@ k4_bulyan_static(const __grid_constant__ RowTable rows, const Geom g, const int3
       key[it] = float_to_key(__fdiv_rn(acc, (float)(M_MAX - it)));
     }
     // Stage 2 (bulyan.py:78-84)
-    SortNet<THETA>::template run<OpsKey>(key);
+    SortNet<THETA>::run(OpsKey{}, key);
     float s[THETA];
 #pragma unroll
     for (int it = 0; it < THETA; ++it) s[it] = key_to_float(key[it]);

@@ -41,14 +41,15 @@ def bitonic_free_oddeven(n):
 
 def prune(net, n, outputs):
   """ Backward liveness: keep only what the wires in `outputs` (after the network) depend on.
-  Returns a list of (a, b, need_min, need_max). """
+  Returns a list of (a, b, need_min, need_max, index in net). """
   live = set(outputs)
   kept = []
-  for (a, b) in reversed(net):
+  for k in range(len(net) - 1, -1, -1):
+    a, b = net[k]
     need_min = a in live
     need_max = b in live
     if need_min or need_max:
-      kept.append((a, b, need_min, need_max))
+      kept.append((a, b, need_min, need_max, k))
       live.add(a)
       live.add(b)
   kept.reverse()
