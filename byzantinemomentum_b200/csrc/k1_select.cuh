@@ -106,8 +106,14 @@ __device__ __forceinline__ void k1_walk(const RowTable& rows, const Geom& g, flo
 
 // ---- median ---------------------------------------------------------------------------
 
+// Register cap: 4 resident CTAs per SM (<= 128 registers) whenever the N x VEC values leave room.
+#ifndef BZ_K1_CAP
+#define BZ_K1_CAP 104
+#endif
+__host__ __device__ constexpr int k1_min_blocks(int n, int vec) { return (n * vec <= BZ_K1_CAP) ? 4 : 1; }
+
 template <int N, int VEC>
-__global__ void __launch_bounds__(kK1Threads)
+__global__ void __launch_bounds__(kK1Threads, k1_min_blocks(N, VEC))
 k1_median(const __grid_constant__ RowTable rows, const Geom g, float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
   k1_walk<N, VEC>(rows, g, smem, [&](float (&x)[VEC][N], int64_t e0, bool full) {
@@ -205,7 +211,7 @@ template <int N, int F, int MODE> struct MixFor { typedef OpsMix<MixFull<N>> typ
 template <int N, int F> struct MixFor<N, F, kModeTrmean> { typedef OpsMix<MixTrim<N, F>> type; };
 
 template <int N, int VEC, int F, int MODE>
-__global__ void __launch_bounds__(kK1Threads)
+__global__ void __launch_bounds__(kK1Threads, k1_min_blocks(N, VEC))
 k1_sorted(const __grid_constant__ RowTable rows, const Geom g, const int mode_rt, const int f_rt,
           float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];   // [stage][+ sorted columns for the closest modes]
