@@ -198,6 +198,23 @@ struct OpsKey {
     a = lo; b = hi;
   }
 };
+// Same pipe split as OpsMix, on integer keys (exact for every input: no NaN caveat).
+template <class Mask>
+struct OpsKeyMix {
+  int one, mone;
+  template <int K> __device__ __forceinline__ void ce(int& a, int& b) const {
+    const int lo = min(a, b);
+    if constexpr (Mask::mix(K)) {
+      int s, h;
+      asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(s) : "r"(a), "r"(one), "r"(b));
+      asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(h) : "r"(lo), "r"(mone), "r"(s));
+      b = h;
+    } else {
+      b = max(a, b);
+    }
+    a = lo;
+  }
+};
 __device__ __forceinline__ int float_to_key(float x) {
   int k = __float_as_int(x);
   k ^= (k >> 31) & 0x7fffffff;

@@ -207,8 +207,8 @@ __device__ __forceinline__ float closest_pairs_static(const float (&s)[N], float
 }
 
 // Mask of the mixed comparators: pruned for a compile-time trimmed mean, full sort otherwise.
-template <int N, int F, int MODE> struct MixFor { typedef OpsMix<MixFull<N>> type; };
-template <int N, int F> struct MixFor<N, F, kModeTrmean> { typedef OpsMix<MixTrim<N, F>> type; };
+template <int N, int F, int MODE> struct MixFor { typedef MixFull<N> mask; typedef OpsMix<mask> type; };
+template <int N, int F> struct MixFor<N, F, kModeTrmean> { typedef MixTrim<N, F> mask; typedef OpsMix<mask> type; };
 
 template <int N, int VEC, int F, int MODE>
 __global__ void __launch_bounds__(kK1Threads, k1_min_blocks(N, VEC))
@@ -242,7 +242,7 @@ k1_sorted(const __grid_constant__ RowTable rows, const Geom g, const int mode_rt
         int k[N];
 #pragma unroll
         for (int r = 0; r < N; ++r) k[r] = float_to_key(x[c][r]);
-        SortNet<N>::run(OpsKey{}, k);
+        SortNet<N>::run(OpsKeyMix<typename MixFor<N, F, MODE>::mask>{g.one, g.mone}, k);
 #pragma unroll
         for (int r = 0; r < N; ++r) x[c][r] = key_to_float(k[r]);
         if (MODE == kModeTrmean) res[c] = trmean_sorted<N>(x[c], f);

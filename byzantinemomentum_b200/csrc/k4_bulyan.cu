@@ -18,7 +18,7 @@ constexpr int kK4Threads = 128;
 
 template <int THETA>
 __global__ void __launch_bounds__(kK4Threads)
-k4_bulyan(const __grid_constant__ RowTable rows, const int64_t d, const int n, const int f, const int m,
+k4_bulyan(const __grid_constant__ RowTable rows, const int64_t d, const int n, const int f, const int m, const int one, const int mone,
           const int32_t* __restrict__ order, const int32_t* __restrict__ status, float* __restrict__ out) {
   extern __shared__ float sm[];   // [max(m_max, THETA)][kK4Threads]
   const int64_t i = (int64_t)blockIdx.x * kK4Threads + threadIdx.x;
@@ -48,7 +48,7 @@ k4_bulyan(const __grid_constant__ RowTable rows, const int64_t d, const int n, c
     key[it] = float_to_key(__fdiv_rn(acc, (float)mi));
   }
   // Stage 2 (bulyan.py:78-84): lower median over theta, beta closest to it, mean
-  SortNet<THETA>::run(OpsKey{}, key);
+  SortNet<THETA>::run(OpsKeyMix<MixFull<THETA>>{one, mone}, key);
   float last = key_to_float(key[THETA - 1]);
   const float med = (last != last) ? quiet_nan() : key_to_float(key[(THETA - 1) / 2]);
 #pragma unroll
@@ -123,7 +123,7 @@ k4_bulyan_static(const __grid_constant__ RowTable rows, const Geom g, const int3
       key[it] = float_to_key(__fdiv_rn(acc, (float)(M_MAX - it)));
     }
     // Stage 2 (bulyan.py:78-84)
-    SortNet<THETA>::run(OpsKey{}, key);
+    SortNet<THETA>::run(OpsKeyMix<MixFull<THETA>>{g.one, g.mone}, key);
     float s[THETA];
 #pragma unroll
     for (int it = 0; it < THETA; ++it) s[it] = key_to_float(key[it]);
@@ -172,7 +172,7 @@ static void launch_theta(const RowTable& rows, int64_t d, int n, int f, int m, c
   const int rowsm = m_max > THETA ? m_max : THETA;
   const size_t smem = (size_t)rowsm * kK4Threads * sizeof(float);
   k4_bulyan<THETA><<<(unsigned)((threads + kK4Threads - 1) / kK4Threads), kK4Threads, smem, st>>>(
-      rows, d, n, f, m, order, status, out);
+      rows, d, n, f, m, 1, -1, order, status, out);
 }
 
 bool launch_bulyan_reduce(const RowTable& rows, int n, int f, int m, const int32_t* order, const int32_t* status,
