@@ -27,7 +27,7 @@ int check_launch(const char* what) {
 }
 
 Geom make_geom(const float* const* rows, int n, const void* out, const void* extra, int64_t d, int want_vec) {
-  Geom g{d, d, 0, 1, 1, -1};
+  Geom g{d, d, 0, 1, 1, -1, 0};
   if (want_vec <= 1 || d < 1) return g;
   const uintptr_t bytes = (uintptr_t)want_vec * sizeof(float);
   const uintptr_t mis = (uintptr_t)rows[0] % bytes;
@@ -90,10 +90,12 @@ int run_sorted(const float* const* rows, int n, int mode, int f, int64_t d, floa
 }
 
 int run_average_selected(const float* const* rows, int n, const int32_t* sel, int count, int zero_init,
-                         float divisor, const int32_t* status, int64_t d, float* out, cudaStream_t st) {
+                         float divisor, const int32_t* status, int64_t d, float* out, cudaStream_t st, int reverse = 0) {
   RowTable t;
   fill_table(t, rows, n);
-  launch_average(t, make_geom(rows, n, out, nullptr, d, 4), sel, count, zero_init, divisor, status, out, st);
+  Geom g = make_geom(rows, n, out, nullptr, d, 4);
+  g.reverse = reverse;
+  launch_average(t, g, sel, count, zero_init, divisor, status, out, st);
   return check_launch("k3_average");
 }
 

@@ -33,6 +33,8 @@ struct Geom {
   int     vec;     // VEC of the launch (host side bookkeeping)
   int     one;     // = 1 and
   int     mone;    // = -1, opaque to the compiler (OpsMix)
+  int     reverse; // walk the vectors from the end: the previous pass over the same rows went
+                   // forward, so its last ~L2-size bytes are still cached (K3 / K4 / K2' after K2)
 };
 
 // Widest usable vector (want_vec, else 1) for these rows / output / optional extra pointer.

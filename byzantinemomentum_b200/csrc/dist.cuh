@@ -31,7 +31,7 @@ int launch_pairdist(const RowTable& rows, int n, int64_t d, double* parts, cudaS
 
 // K2': parts[x*n + i] = share of sum_k (rows[i][k] - center[k])^2 (center NULL: the origin).
 int launch_rowdist(const RowTable& rows, int n, const float* const* host_rows, const float* center, int64_t d,
-                   double* parts, cudaStream_t st);
+                   double* parts, cudaStream_t st, int reverse = 0);
 
 // Sum `nparts` blocks of `len` doubles in index order into `block` (fixed order: deterministic).
 // pair_n > 0: the block is a pair_n x pair_n table of which only entries i < j are defined; the

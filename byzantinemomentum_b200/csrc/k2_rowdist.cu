@@ -34,7 +34,9 @@ k2_rowdist(const __grid_constant__ RowTable rows, const int n, const float* __re
   // warp-uniform trip count: lanes past the end contribute zeros and still join the shuffles
   const int64_t first = (int64_t)blockIdx.x * kRdThreads + warp * 32;
   int pending = 0;
-  for (int64_t vb = first; vb < g.nv; vb += stride) {
+  for (int64_t vf = first; vf < g.nv; vf += stride) {
+    // reversed walk (Geom::reverse): same warp-uniform trip count, mirrored base
+    const int64_t vb = g.reverse ? ((g.nv - 1) / 32) * 32 - vf : vf;
     const int64_t v = vb + lane;
     const bool live = v < g.nv;
     const int64_t e0 = v * VEC - g.shift;
@@ -111,9 +113,10 @@ static int rd_sm_count() {
 }
 
 int launch_rowdist(const RowTable& rows, int n, const float* const* host_rows, const float* center, int64_t d,
-                   double* parts, cudaStream_t st) {
+                   double* parts, cudaStream_t st, int reverse) {
   // The centre doubles as the alignment reference ("out") of the geometry
-  const Geom g = make_geom(host_rows, n, center ? (const void*)center : (const void*)host_rows[0], nullptr, d, 4);
+  Geom g = make_geom(host_rows, n, center ? (const void*)center : (const void*)host_rows[0], nullptr, d, 4);
+  g.reverse = reverse;
   int64_t grid = (g.nv + kRdThreads - 1) / kRdThreads;
   const int64_t cap = (int64_t)rd_sm_count() * 2;
   if (grid > cap) grid = cap;

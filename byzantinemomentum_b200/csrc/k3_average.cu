@@ -57,7 +57,8 @@ __global__ void __launch_bounds__(kK3Threads)
 k3_average(const __grid_constant__ RowTable rows, const Geom g, const int32_t* __restrict__ sel,
            const int count, const int zero_init, const float divisor,
            const int32_t* __restrict__ status, float* __restrict__ out) {
-  const int64_t v = (int64_t)blockIdx.x * kK3Threads + threadIdx.x;
+  const int64_t blk = g.reverse ? (int64_t)gridDim.x - 1 - blockIdx.x : (int64_t)blockIdx.x;
+  const int64_t v = blk * kK3Threads + threadIdx.x;
   if (v >= g.nv) return;
   const int64_t e0 = v * VEC - g.shift;
   const bool full = e0 >= 0 && e0 + VEC <= g.d;

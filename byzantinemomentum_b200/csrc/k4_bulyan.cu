@@ -21,7 +21,8 @@ __global__ void __launch_bounds__(kK4Threads)
 k4_bulyan(const __grid_constant__ RowTable rows, const int64_t d, const int n, const int f, const int m, const int one, const int mone,
           const int32_t* __restrict__ order, const int32_t* __restrict__ status, float* __restrict__ out) {
   extern __shared__ float sm[];   // [max(m_max, THETA)][kK4Threads]
-  const int64_t i = (int64_t)blockIdx.x * kK4Threads + threadIdx.x;
+  // reversed walk: the distance pass before this one went forward (see Geom::reverse)
+  const int64_t i = ((int64_t)gridDim.x - 1 - blockIdx.x) * kK4Threads + threadIdx.x;
   if (i >= d) return;
   const int64_t e = i;
   if (status != nullptr && *status != 0) { out[e] = quiet_nan(); return; }
@@ -82,7 +83,8 @@ __global__ void __launch_bounds__(kK4Threads)
 k4_bulyan_static(const __grid_constant__ RowTable rows, const Geom g, const int32_t* __restrict__ order,
                  const int32_t* __restrict__ status, float* __restrict__ out) {
   constexpr int M_MAX = N - F - 2, THETA = N - 2 * F - 2, BETA = THETA - 2 * F, R = THETA - BETA;
-  const int64_t v = (int64_t)blockIdx.x * kK4Threads + threadIdx.x;
+  const int64_t blk = g.reverse ? (int64_t)gridDim.x - 1 - blockIdx.x : (int64_t)blockIdx.x;
+  const int64_t v = blk * kK4Threads + threadIdx.x;
   if (v >= g.nv) return;
   const int64_t e0 = v * VEC - g.shift;
   const bool full = e0 >= 0 && e0 + VEC <= g.d;
