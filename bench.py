@@ -116,9 +116,13 @@ def make_rows(torch, n, d, device, seed, sets):
   gen = torch.Generator(device=device).manual_seed(seed)
   return [[torch.randn(d, device=device, generator=gen) for _ in range(n)] for _ in range(sets)]
 
+EXCHANGE = "nccl"
+
 def call_device(bz, sharded, gar, rows, f, world):
   """ One aggregation of device-resident rows (the step of the timed region). """
   if world > 1:
+    if EXCHANGE == "p2p":
+      return sharded.aggregate_p2p(gar, rows, f=f)
     return sharded.aggregate(gar, rows, f=f)
   return bz.gars[gar].unchecked(gradients=rows, f=f)
 
@@ -246,7 +250,7 @@ def run_b200(args):
     api = f"byzantinemomentum_b200.Plan({gar!r}, rows, f={f})()"
   else:
     step = lambda k: call_device(bz, sharded, gar, inputs[k % sets], f, world)
-    api = f"byzantinemomentum_b200.sharded.aggregate({gar!r}, rows, f={f})"
+    api = f"byzantinemomentum_b200.sharded.aggregate{'_p2p' if EXCHANGE == 'p2p' else ''}({gar!r}, rows, f={f})"
   for k in range(max(args.warmup, 3)):
     step(k)
   barrier()
@@ -400,7 +404,11 @@ def main():
   ap.add_argument("--nb-byz", dest="f", type=int, default=10)
   ap.add_argument("--dim", dest="d", type=int, default=1_310_922)
   ap.add_argument("--no-sweep", action="store_true")
+  ap.add_argument("--exchange", choices=("nccl", "p2p"), default="nccl",
+                  help="N > 1, distance-based rules: all-gather (NCCL) or blocks read in place over NVLink peer memory")
   args = ap.parse_args()
+  global EXCHANGE
+  EXCHANGE = args.exchange
   if args.impl == "reference":
     run_reference(args)
   else:

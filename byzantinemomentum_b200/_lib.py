@@ -15,6 +15,7 @@ __all__ = ["lib", "LibraryError", "library_path", "check", "MAX_N", "STATUS_MESS
            "AKSEL_MODES", "STATUS_NO_FINITE_SET", "STATUS_DEGENERATE"]
 
 MAX_N = 64
+MAX_PEERS = 16
 STATUS_NO_FINITE_SET = 1
 STATUS_DEGENERATE = 2
 STATUS_MESSAGES = {
@@ -57,6 +58,10 @@ SIGNATURES = {
   "bz_bulyan_select": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
   "bz_brute_select": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
   "bz_rowdist_select": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+  "bz_krum_select_peers": (_i, [_c_rows, _i, _i, _i, _vp, _vp]),
+  "bz_bulyan_select_peers": (_i, [_c_rows, _i, _i, _i, _i, _vp, _vp, _vp]),
+  "bz_brute_select_peers": (_i, [_c_rows, _i, _i, _i, _vp, _vp, _vp]),
+  "bz_rowdist_select_peers": (_i, [_c_rows, _i, _i, _i, _vp, _vp]),
   "bz_average_selected": (_i, [_c_rows, _i, _vp, _i, _i, _dbl, _vp, _i64, _vp, _vp]),
   "bz_bulyan_reduce": (_i, [_c_rows, _i, _i, _i, _vp, _vp, _i64, _vp, _vp]),
 }

@@ -44,6 +44,12 @@ void launch_bulyan_select(const double* parts, int nparts, int n, int f, int m, 
 int  launch_brute_select(const double* parts, int nparts, int n, int f, int32_t* sel, int32_t* status, cudaStream_t st);
 void launch_rowdist_select(const double* parts, int nparts, int n, int sqrt_norm, int32_t* order, cudaStream_t st);
 
+// Same, reading block p IN PLACE from peers[p] (peer GPU memory over NVLink): fused exchange.
+void launch_krum_select_peers(const double* const* peers, int npeers, int n, int f, int32_t* order, cudaStream_t st);
+void launch_bulyan_select_peers(const double* const* peers, int npeers, int n, int f, int m, int32_t* order, int32_t* status, cudaStream_t st);
+int  launch_brute_select_peers(const double* const* peers, int npeers, int n, int f, int32_t* sel, int32_t* status, cudaStream_t st);
+void launch_rowdist_select_peers(const double* const* peers, int npeers, int n, int sqrt_norm, int32_t* order, cudaStream_t st);
+
 // ---- K4: Bulyan stage 1 means + coordinate-wise averaged median ----------------------------------
 bool launch_bulyan_reduce(const RowTable& rows, int n, int f, int m, const int32_t* order, const int32_t* status,
                           int64_t d, float* out, cudaStream_t st);

@@ -15,6 +15,21 @@ constexpr int kK5Threads = 1024;
 
 __device__ __forceinline__ bool finite_d(double x) { return fabs(x) <= 1.7976931348623157e308; }
 
+// Where the partial blocks live: one strided buffer (per-CTA blocks of K2 / K2', or blocks gathered
+// by a collective), or one pointer per peer GPU — the blocks are then read IN PLACE from the
+// peers' memory over NVLink (ld.global on peer-mapped addresses): the exchange step of the
+// d-sharded path is fused into the scoring kernel, no all-gather, no staging copy.
+struct StridedParts {
+  const double* base;
+  size_t stride;
+  __device__ __forceinline__ const double* block(int p) const { return base + (size_t)p * stride; }
+};
+constexpr int kMaxPeers = BZ_MAX_PEERS;
+struct PeerParts {
+  const double* ptr[kMaxPeers];
+  __device__ __forceinline__ const double* block(int p) const { return ptr[p]; }
+};
+
 // Block-wide, deterministic sum of `nparts` partial blocks of `len` doubles into smem `out`.
 // The parts are split in `slices` interleaved classes (p mod slices); thread (slice, t) walks
 // entries t, t + T, ... and adds its class in ascending p; the classes are then added in
@@ -22,7 +37,8 @@ __device__ __forceinline__ bool finite_d(double x) { return fabs(x) <= 1.7976931
 // same on every rank of the sharded path.  All loads of a thread are independent across
 // entries, so a thread keeps several in flight (the naive per-entry loop over 148 parts cost
 // ~20 us of pure latency).
-__device__ void block_sum_parts(const double* __restrict__ parts, int nparts, int len, int slices,
+template <class Parts>
+__device__ void block_sum_parts(const Parts& parts, int nparts, int len, int slices,
                                 double* __restrict__ scratch, double* __restrict__ out) {
   const int T = blockDim.x / slices;            // threads per slice
   const int slice = threadIdx.x / T, t = threadIdx.x - slice * T;
@@ -34,7 +50,7 @@ __device__ void block_sum_parts(const double* __restrict__ parts, int nparts, in
       for (int q = 0; q < E; ++q) s[q] = 0.;
 #pragma unroll 4
       for (int p = slice; p < nparts; p += slices) {
-        const double* __restrict__ row = parts + (size_t)p * len;
+        const double* __restrict__ row = parts.block(p);
 #pragma unroll
         for (int q = 0; q < E; ++q) {
           const int e = e0 + q * T;
@@ -128,8 +144,9 @@ __device__ void stable_order(const double* key, int n, int32_t* __restrict__ ord
 // krum.py:52-62 (count = n-f-1, diagonal excluded) and bulyan.py:56-62 (count = m over the
 // row INCLUDING its +inf diagonal).  Putting +inf on the diagonal serves both: the extra +inf
 // can only be reached after every finite distance, where the sum is +inf either way.
+template <class Parts>
 __global__ void __launch_bounds__(kK5Threads)
-k5_score_select(const double* __restrict__ parts, int nparts, int n, int count, int32_t* __restrict__ order,
+k5_score_select(const __grid_constant__ Parts parts, int nparts, int n, int count, int32_t* __restrict__ order,
                 int32_t* __restrict__ status, int f, int m, int bulyan, int slices) {
   extern __shared__ double sm[];
   double* dist = sm;
@@ -162,8 +179,9 @@ k5_score_select(const double* __restrict__ parts, int nparts, int n, int count, 
 
 // aksel.py:39-49 / cge.py:28-38: stable order of n keys.
 constexpr int kRowSelThreads = 1024, kRowSelSlices = 16;   // 64 threads per slice: one per row
+template <class Parts>
 __global__ void __launch_bounds__(kRowSelThreads)
-k5_rowdist_select(const double* __restrict__ parts, int nparts, int n, int sqrt_norm, int32_t* __restrict__ order) {
+k5_rowdist_select(const __grid_constant__ Parts parts, int nparts, int n, int sqrt_norm, int32_t* __restrict__ order) {
   __shared__ double key[kMaxN];
   __shared__ double scratch[kRowSelSlices * kMaxN];
   block_sum_parts(parts, nparts, n, kRowSelSlices, scratch, key);
@@ -190,8 +208,9 @@ __device__ __forceinline__ unsigned long long sat_add(unsigned long long a, unsi
   return s < a ? ~0ull : s;
 }
 
+template <class Parts>
 __global__ void __launch_bounds__(kK5Threads)
-k5_brute_select(const double* __restrict__ parts, int nparts, int n, int f, unsigned long long total,
+k5_brute_select(const __grid_constant__ Parts parts, int nparts, int n, int f, unsigned long long total,
                 int32_t* __restrict__ sel, int32_t* __restrict__ status, int slices) {
   extern __shared__ double sm[];
   double* dist = sm;                                                  // n*n
@@ -319,23 +338,18 @@ static void opt_in_once(K kernel, size_t bytes, unsigned long long& mask) {
 constexpr size_t kScoreSmemMax = (size_t)(2 * kMaxN * kMaxN + kMaxN) * sizeof(double) + 48 * 1024;
 constexpr size_t kBruteSmemMax = (size_t)kMaxN * kMaxN * sizeof(double) + (size_t)(kMaxN + 1) * (kMaxN + 1) * sizeof(unsigned long long) + 48 * 1024;
 
-void launch_krum_select(const double* parts, int nparts, int n, int f, int32_t* order, cudaStream_t st) {
+template <class Parts>
+static void score_select(const Parts& parts, int nparts, int n, int count, int32_t* order, int32_t* status, int f, int m,
+                         int bulyan, cudaStream_t st) {
   const int slices = pick_slices(n, nparts);
   const size_t smem = (size_t)(2 * n * n + n + slices * n * n) * sizeof(double);
   static unsigned long long opted = 0;
-  opt_in_once(k5_score_select, kScoreSmemMax, opted);
-  k5_score_select<<<1, kK5Threads, smem, st>>>(parts, nparts, n, n - f - 1, order, nullptr, f, 0, 0, slices);
+  opt_in_once(k5_score_select<Parts>, kScoreSmemMax, opted);
+  k5_score_select<Parts><<<1, kK5Threads, smem, st>>>(parts, nparts, n, count, order, status, f, m, bulyan, slices);
 }
 
-void launch_bulyan_select(const double* parts, int nparts, int n, int f, int m, int32_t* order, int32_t* status, cudaStream_t st) {
-  const int slices = pick_slices(n, nparts);
-  const size_t smem = (size_t)(2 * n * n + n + slices * n * n) * sizeof(double);
-  static unsigned long long opted = 0;
-  opt_in_once(k5_score_select, kScoreSmemMax, opted);
-  k5_score_select<<<1, kK5Threads, smem, st>>>(parts, nparts, n, m, order, status, f, m, 1, slices);
-}
-
-int launch_brute_select(const double* parts, int nparts, int n, int f, int32_t* sel, int32_t* status, cudaStream_t st) {
+template <class Parts>
+static int brute_select(const Parts& parts, int nparts, int n, int f, int32_t* sel, int32_t* status, cudaStream_t st) {
   // C(n, n-f) on the host, saturating
   const int k = n - f;
   unsigned long long total = 1;
@@ -349,13 +363,42 @@ int launch_brute_select(const double* parts, int nparts, int n, int f, int32_t* 
   const size_t smem = (size_t)n * n * sizeof(double) + (size_t)(n + 1) * (n + 1) * sizeof(unsigned long long) +
                       (size_t)slices * n * n * sizeof(double);
   static unsigned long long opted = 0;
-  opt_in_once(k5_brute_select, kBruteSmemMax, opted);
-  k5_brute_select<<<1, kK5Threads, smem, st>>>(parts, nparts, n, f, total, sel, status, slices);
+  opt_in_once(k5_brute_select<Parts>, kBruteSmemMax, opted);
+  k5_brute_select<Parts><<<1, kK5Threads, smem, st>>>(parts, nparts, n, f, total, sel, status, slices);
   return 0;
 }
 
+static PeerParts make_peers(const double* const* ptrs, int npeers) {
+  PeerParts p;
+  for (int r = 0; r < kMaxPeers; ++r) p.ptr[r] = ptrs[r < npeers ? r : 0];
+  return p;
+}
+
+void launch_krum_select(const double* parts, int nparts, int n, int f, int32_t* order, cudaStream_t st) {
+  score_select(StridedParts{parts, (size_t)n * n}, nparts, n, n - f - 1, order, nullptr, f, 0, 0, st);
+}
+void launch_bulyan_select(const double* parts, int nparts, int n, int f, int m, int32_t* order, int32_t* status, cudaStream_t st) {
+  score_select(StridedParts{parts, (size_t)n * n}, nparts, n, m, order, status, f, m, 1, st);
+}
+int launch_brute_select(const double* parts, int nparts, int n, int f, int32_t* sel, int32_t* status, cudaStream_t st) {
+  return brute_select(StridedParts{parts, (size_t)n * n}, nparts, n, f, sel, status, st);
+}
 void launch_rowdist_select(const double* parts, int nparts, int n, int sqrt_norm, int32_t* order, cudaStream_t st) {
-  k5_rowdist_select<<<1, kRowSelThreads, 0, st>>>(parts, nparts, n, sqrt_norm, order);
+  k5_rowdist_select<StridedParts><<<1, kRowSelThreads, 0, st>>>(StridedParts{parts, (size_t)n}, nparts, n, sqrt_norm, order);
+}
+
+// Peer variants: block p is read from peers[p] (NVLink peer memory)
+void launch_krum_select_peers(const double* const* peers, int npeers, int n, int f, int32_t* order, cudaStream_t st) {
+  score_select(make_peers(peers, npeers), npeers, n, n - f - 1, order, nullptr, f, 0, 0, st);
+}
+void launch_bulyan_select_peers(const double* const* peers, int npeers, int n, int f, int m, int32_t* order, int32_t* status, cudaStream_t st) {
+  score_select(make_peers(peers, npeers), npeers, n, m, order, status, f, m, 1, st);
+}
+int launch_brute_select_peers(const double* const* peers, int npeers, int n, int f, int32_t* sel, int32_t* status, cudaStream_t st) {
+  return brute_select(make_peers(peers, npeers), npeers, n, f, sel, status, st);
+}
+void launch_rowdist_select_peers(const double* const* peers, int npeers, int n, int sqrt_norm, int32_t* order, cudaStream_t st) {
+  k5_rowdist_select<PeerParts><<<1, kRowSelThreads, 0, st>>>(make_peers(peers, npeers), npeers, n, sqrt_norm, order);
 }
 
 }  // namespace bz

@@ -362,6 +362,62 @@ def rowdist_select(parts, n, sqrt_norm):
   _lib.check(code, "bz_rowdist_select")
   return meta[:n]
 
+# Peer-memory variants of phase B: `peer_ptrs` is a list of R device addresses (one per rank, rank
+# order) of the ranks' partial blocks, mapped over NVLink; the blocks are read in place.
+
+def _peers(peer_ptrs, n, device):
+  if not 1 <= len(peer_ptrs) <= _lib.MAX_PEERS:
+    raise ValueError(f"{len(peer_ptrs)} peers, expected 1..{_lib.MAX_PEERS}")
+  table = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+  meta = torch.empty(n + 1, dtype=torch.int32, device=device)
+  return table, meta, torch.cuda.current_stream(device).cuda_stream
+
+def krum_select_peers(peer_ptrs, n, f, device):
+  table, meta, stream = _peers(peer_ptrs, n, device)
+  with _on(device):
+    code = _lib.lib().bz_krum_select_peers(table, len(peer_ptrs), n, int(f), meta.data_ptr(), stream)
+  _lib.check(code, "bz_krum_select_peers")
+  return meta[:n]
+
+def bulyan_select_peers(peer_ptrs, n, f, m, device):
+  table, meta, stream = _peers(peer_ptrs, n, device)
+  with _on(device):
+    code = _lib.lib().bz_bulyan_select_peers(table, len(peer_ptrs), n, int(f), int(m), meta.data_ptr(), meta[n:].data_ptr(), stream)
+  _lib.check(code, "bz_bulyan_select_peers")
+  return meta[:n], meta[n:]
+
+def brute_select_peers(peer_ptrs, n, f, device):
+  table, meta, stream = _peers(peer_ptrs, n, device)
+  with _on(device):
+    code = _lib.lib().bz_brute_select_peers(table, len(peer_ptrs), n, int(f), meta.data_ptr(), meta[n:].data_ptr(), stream)
+  _lib.check(code, "bz_brute_select_peers")
+  return meta[:n - int(f)], meta[n:]
+
+def rowdist_select_peers(peer_ptrs, n, sqrt_norm, device):
+  table, meta, stream = _peers(peer_ptrs, n, device)
+  with _on(device):
+    code = _lib.lib().bz_rowdist_select_peers(table, len(peer_ptrs), n, 1 if sqrt_norm else 0, meta.data_ptr(), stream)
+  _lib.check(code, "bz_rowdist_select_peers")
+  return meta[:n]
+
+def pairdist_partial_into(gradients, part):
+  """ Phase A writing straight into `part` (e.g. this rank's slot of a symmetric buffer). """
+  prep = _prepare_device(gradients)
+  ws = _workspace(prep.device, prep.stream)
+  with _on(prep.device):
+    code = _lib.lib().bz_pairdist_partial(prep.ptrs, prep.n, prep.d, part.data_ptr(), ws.data_ptr(), ws.numel(), prep.stream)
+  _lib.check(code, "bz_pairdist_partial")
+  return part
+
+def rowdist_partial_into(gradients, center, part):
+  prep = _prepare_device(gradients)
+  ws = _workspace(prep.device, prep.stream)
+  cptr = None if center is None else center.data_ptr()
+  with _on(prep.device):
+    code = _lib.lib().bz_rowdist_partial(prep.ptrs, prep.n, cptr, prep.d, part.data_ptr(), ws.data_ptr(), ws.numel(), prep.stream)
+  _lib.check(code, "bz_rowdist_partial")
+  return part
+
 def average_selected(gradients, selection, count, zero_init=True, divisor=None, status=None):
   """ Ordered-subset average of the local shard; `selection` is a device int32 tensor or None. """
   prep = _prepare_device(gradients)

@@ -27,7 +27,7 @@ import torch.distributed as dist
 
 from . import engine as _engine
 
-__all__ = ["aggregate", "COORDINATE_WISE", "DISTANCE_BASED"]
+__all__ = ["aggregate", "aggregate_p2p", "PeerExchange", "COORDINATE_WISE", "DISTANCE_BASED"]
 
 COORDINATE_WISE = ("average", "median", "trmean", "phocas", "meamed")
 DISTANCE_BASED = ("krum", "bulyan", "brute", "aksel", "cge")
@@ -40,6 +40,86 @@ def _gather(part, group):
   gathered = torch.empty((world,) + tuple(part.shape), dtype=part.dtype, device=part.device)
   dist.all_gather([gathered[r] for r in range(world)], part.contiguous(), group=group)
   return gathered
+
+class PeerExchange:
+  """ Exchange of the partial blocks through NVLink peer memory instead of a collective.
+
+  Every rank owns two slots of n*n doubles in a SYMMETRIC buffer (torch symmetric memory: the
+  same allocation mapped into every rank's address space over NVLink/NVSwitch).  A step writes
+  its block into slot `step % 2` (phase A writes there directly), crosses ONE device-side
+  barrier, and the selection kernel then reads the R blocks in place from the R ranks
+  (`bz_*_select_peers`): gather and scoring are one kernel.  Two slots make one barrier per
+  step enough: a rank can only reach the barrier of step t+1 after its reads of step t, so by
+  the time slot t%2 is rewritten (step t+2) every peer has finished reading it.
+  Needs CUDA peer access between the ranks' GPUs (one NVSwitch domain) and <= 16 ranks. """
+  def __init__(self, n, device, group=None):
+    import torch.distributed._symmetric_memory as symm_mem
+    self.n = n
+    self.device = device
+    self.group = group if group is not None else dist.group.WORLD
+    self.world = dist.get_world_size(self.group)
+    self.buffer = symm_mem.empty(2 * n * n, dtype=torch.float64, device=device)
+    self.handle = symm_mem.rendezvous(self.buffer, self.group)
+    self.peer_base = [int(p) for p in self.handle.buffer_ptrs]
+    self.step = 0
+  def slot(self):
+    """ (this rank's slot as a tensor, the R peers' addresses of the same slot) for this step. """
+    off = (self.step % 2) * self.n * self.n
+    mine = self.buffer[off:off + self.n * self.n]
+    return mine, [base + off * 8 for base in self.peer_base]
+  def publish(self):
+    """ Order every rank's phase-A writes before anyone's reads (stream-ordered device barrier). """
+    self.handle.barrier(channel=0)
+    self.step += 1
+
+_exchanges = {}
+
+def peer_exchange(n, device, group=None):
+  key = (n, device.index, id(group))
+  ex = _exchanges.get(key)
+  if ex is None:
+    ex = _exchanges[key] = PeerExchange(n, device, group)
+  return ex
+
+def aggregate_p2p(gar, gradients, f=None, m=None, mode="mid", group=None, return_selection=False):
+  """ `aggregate` for the distance-based rules with the exchange fused into the selection kernel
+  (peer memory over NVLink, see PeerExchange).  CUDA engine only. """
+  be = _engine
+  n = len(gradients)
+  if gar in COORDINATE_WISE:
+    return aggregate(gar, gradients, f=f, m=m, mode=mode, group=group, return_selection=return_selection)
+  device = gradients[0].device
+  ex = peer_exchange(n, device, group)
+  mine, peers = ex.slot()
+  if gar in ("krum", "bulyan", "brute"):
+    be.pairdist_partial_into(gradients, mine)
+    ex.publish()
+    if gar == "krum":
+      m = n - f - 2 if m is None else m
+      sel = be.krum_select_peers(peers, n, f, device)
+      out = be.average_selected(gradients, sel, m)
+    elif gar == "bulyan":
+      m = n - f - 2 if m is None else m
+      sel, status = be.bulyan_select_peers(peers, n, f, m, device)
+      out = be.bulyan_reduce(gradients, f, m, sel, status)
+    else:
+      sel, status = be.brute_select_peers(peers, n, f, device)
+      out = be.average_selected(gradients, sel, n - f, status=status)
+  elif gar == "aksel":
+    count = (n + 1) // 2 if mode == "mid" else n - f
+    center = be.median(gradients)
+    be.rowdist_partial_into(gradients, center, mine[:n])
+    ex.publish()
+    sel = be.rowdist_select_peers(peers, n, False, device)
+    out = be.average_selected(gradients, sel, count)
+  elif gar == "cge":
+    be.rowdist_partial_into(gradients, None, mine[:n])
+    ex.publish()
+    sel = be.rowdist_select_peers(peers, n, True, device)
+    out = be.average_selected(gradients, sel, n - f, zero_init=False)
+  else:
+    raise KeyError(f"unknown aggregation rule {gar!r}")
+  return (out, sel) if return_selection else out
 
 def aggregate(gar, gradients, f=None, m=None, mode="mid", group=None, backend=None, return_selection=False):
   """ Aggregate this rank's shard.

@@ -45,6 +45,7 @@ extern "C" {
 #endif
 
 #define BZ_MAX_N 64
+#define BZ_MAX_PEERS 16   /* ranks whose partial blocks one selection kernel can read in place */
 
 #define BZ_OK            0
 #define BZ_EINVAL       -1   /* bad argument (null pointer, n/f/m out of executable range) */
@@ -123,6 +124,19 @@ BZ_API int bz_brute_select(const double* parts, int nparts, int n, int f, int32_
  * sqrt_norm == 0: keys are fl32(sum) (aksel.py:41).  Stable ascending order of the n keys. */
 BZ_API int bz_rowdist_select(const double* parts, int nparts, int n, int sqrt_norm, int32_t* order,
                       void* stream);
+/* B over PEER MEMORY: same selections, but block p is read in place from peers[p], a device
+ *    pointer into rank p's memory mapped over NVLink (e.g. torch symmetric memory): the exchange
+ *    step is fused into the selection kernel, no all-gather.  peers: HOST array of npeers device
+ *    pointers (double[n*n] or double[n] each), npeers <= BZ_MAX_PEERS; the caller orders the
+ *    ranks' writes before the reads (a barrier) and the reads before the next overwrite. */
+BZ_API int bz_krum_select_peers(const double* const* peers, int npeers, int n, int f, int32_t* order,
+                                void* stream);
+BZ_API int bz_bulyan_select_peers(const double* const* peers, int npeers, int n, int f, int m,
+                                  int32_t* order, int32_t* status, void* stream);
+BZ_API int bz_brute_select_peers(const double* const* peers, int npeers, int n, int f, int32_t* sel,
+                                 int32_t* status, void* stream);
+BZ_API int bz_rowdist_select_peers(const double* const* peers, int npeers, int n, int sqrt_norm,
+                                   int32_t* order, void* stream);
 /* C: out = (((z + g[sel[0]]) + g[sel[1]]) + ...) / divisor over the local shard; z = 0.0f when
  *    zero_init (Python sum(), krum.py:80) else the first row itself (cge.py:53).  sel: device
  *    int32[count], or NULL for 0..count-1; divisor is rounded to fp32 (normally = count).

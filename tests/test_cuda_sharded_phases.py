@@ -39,6 +39,10 @@ def test_phases_compose_to_the_single_device_result(n, nb, f, d, R):
   m = n - f - 2
   assert [min(i, n - nb) for i in order.cpu().tolist()[:m]] == [min(i, n - nb) for i in info["selection"]]
   parity.assert_bit_exact(cat([engine.average_selected(s, order, m) for s in shards]), ref, "krum sharded")
+  # phase B reading the R blocks in place through a pointer per "peer" (here: R buffers on one GPU)
+  blocks = [parts[k].contiguous() for k in range(R)]
+  order_p = engine.krum_select_peers([b.data_ptr() for b in blocks], n, f, full[0].device)
+  assert order_p.cpu().tolist() == order.cpu().tolist()
   # same selection as the single-device call
   out1, order1 = engine.krum(full, f, m)
   assert order1.cpu().tolist()[:m] == order.cpu().tolist()[:m]
@@ -59,6 +63,7 @@ def test_phases_compose_to_the_single_device_result(n, nb, f, d, R):
   # cge
   pn = torch.stack([engine.rowdist_partial(s) for s in shards])
   order_c = engine.rowdist_select(pn, n, True)
+  assert engine.rowdist_select_peers([pn[k].contiguous().data_ptr() for k in range(R)], n, True, full[0].device).cpu().tolist() == order_c.cpu().tolist() if R <= 16 else True
   refc = orc.cge(np_rows, f)
   parity.assert_bit_exact(cat([engine.average_selected(s, order_c, n - f, zero_init=False) for s in shards]), refc, "cge sharded")
   # aksel: the median is coordinate-local
