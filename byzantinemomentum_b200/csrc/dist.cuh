@@ -27,7 +27,9 @@ bool carve_workspace(void* ws, size_t bytes, int n, Workspace& out);
 // ---- K2: partial squared pairwise distances -------------------------------------------------
 // parts[x*n*n + i*n + j] (i < j) = this CTA's share of sum_k (rows[i][k] - rows[j][k])^2.
 // Returns the number of partial blocks written (grid size along x), <= kMaxParts.
-int launch_pairdist(const RowTable& rows, int n, int64_t d, double* parts, cudaStream_t st);
+// self_pairs: also write the diagonal entries i == j (sum of (x_i - x_i)^2: 0 or NaN), needed by
+// the alias map of K5.
+int launch_pairdist(const RowTable& rows, int n, int64_t d, double* parts, cudaStream_t st, int self_pairs = 0);
 
 // K2': parts[x*n + i] = share of sum_k (rows[i][k] - center[k])^2 (center NULL: the origin).
 int launch_rowdist(const RowTable& rows, int n, const float* const* host_rows, const float* center, int64_t d,
@@ -39,9 +41,11 @@ int launch_rowdist(const RowTable& rows, int n, const float* const* host_rows, c
 void launch_reduce_parts(const double* parts, int nparts, int len, int pair_n, double* block, cudaStream_t st);
 
 // ---- K5: scoring / selection (single CTA each) --------------------------------------------------
-void launch_krum_select(const double* parts, int nparts, int n, int f, int32_t* order, cudaStream_t st);
-void launch_bulyan_select(const double* parts, int nparts, int n, int f, int m, int32_t* order, int32_t* status, cudaStream_t st);
-int  launch_brute_select(const double* parts, int nparts, int n, int f, int32_t* sel, int32_t* status, cudaStream_t st);
+// to_unique[n] / u: optional alias map (rows i, j with to_unique[i] == to_unique[j] are the same
+// tensor); the blocks are then u x u tables over the unique rows.
+void launch_krum_select(const double* parts, int nparts, int n, int f, int32_t* order, cudaStream_t st, const int* to_unique = nullptr, int u = 0);
+void launch_bulyan_select(const double* parts, int nparts, int n, int f, int m, int32_t* order, int32_t* status, cudaStream_t st, const int* to_unique = nullptr, int u = 0);
+int  launch_brute_select(const double* parts, int nparts, int n, int f, int32_t* sel, int32_t* status, cudaStream_t st, const int* to_unique = nullptr, int u = 0);
 void launch_rowdist_select(const double* parts, int nparts, int n, int sqrt_norm, int32_t* order, cudaStream_t st);
 
 // Same, reading block p IN PLACE from peers[p] (peer GPU memory over NVLink): fused exchange.

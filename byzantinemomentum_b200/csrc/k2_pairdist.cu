@@ -77,7 +77,10 @@ __device__ __forceinline__ void stage_tile(float* buf, const RowTable& rows, int
   }
 }
 
-template <bool DIAG>
+// DIAG: both groups are the same (pairs i < j only; with SELF also i == j: the "distance" of a
+// row to itself, 0 for a finite row and NaN for a row holding NaN / inf — what the reference
+// gets from x.sub(x).norm() for aliased rows; needed when aliases are de-duplicated).
+template <bool DIAG, bool SELF = false>
 __device__ __forceinline__ void sweep_tile(const float* buf, int T, const int (&oa)[kG], const int (&ob)[kG],
                                            int lane, u64 (&acc)[kG * kG]) {
   for (int c = lane * 4; c < T; c += kStep) {
@@ -106,13 +109,28 @@ __device__ __forceinline__ void sweep_tile(const float* buf, int T, const int (&
 #pragma unroll
       for (int i = 0; i < kG; ++i)
 #pragma unroll
-        for (int j = i + 1; j < kG; ++j) {
+        for (int j = i + (SELF ? 0 : 1); j < kG; ++j) {
           const u64 d0 = sub2(a0[i], a0[j]), d1 = sub2(a1[i], a1[j]);
           acc[p] = fma2(d0, d0, acc[p]);
           acc[p] = fma2(d1, d1, acc[p]);
           ++p;
         }
     }
+  }
+}
+
+// lane p -> p-th pair of a diagonal task, row-major; i < j (10 pairs) or i <= j (15 pairs, SELF)
+__device__ __forceinline__ void diag_pair(int lane, bool self, int& i, int& j, bool& valid) {
+  if (self) {
+    i = (lane >= 14) ? 4 : (lane >= 12) ? 3 : (lane >= 9) ? 2 : (lane >= 5) ? 1 : 0;
+    const int first = (i == 0) ? 0 : (i == 1) ? 5 : (i == 2) ? 9 : (i == 3) ? 12 : 14;
+    j = lane - first + i;
+    valid = lane < 15;
+  } else {
+    i = (lane >= 9) ? 3 : (lane >= 7) ? 2 : (lane >= 4) ? 1 : 0;
+    const int first = (i == 0) ? 0 : (i == 1) ? 4 : (i == 2) ? 7 : 9;
+    j = lane - first + i + 1;
+    valid = lane < 10;
   }
 }
 
@@ -128,7 +146,7 @@ __device__ __forceinline__ void flush(u64 (&acc)[kG * kG], int lane, double& dac
 
 __global__ void __launch_bounds__(kK2Threads, 1)
 k2_pairdist(const __grid_constant__ RowTable rows, const int n, const int T, const int logq, const int64_t d,
-            const int64_t ntiles, double* __restrict__ parts) {
+            const int64_t ntiles, const int self_pairs, double* __restrict__ parts) {
   extern __shared__ __align__(16) float smem[];   // [2][n][T]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ng = (n + kG - 1) / kG;
@@ -166,8 +184,9 @@ k2_pairdist(const __grid_constant__ RowTable rows, const int n, const int T, con
     __syncthreads();
     if (active) {
       const float* buf = smem + cur * stage_floats;
-      if (diag) { sweep_tile<true>(buf, T, oa, ob, lane, acc); flush<10>(acc, lane, dacc); }
-      else      { sweep_tile<false>(buf, T, oa, ob, lane, acc); flush<kG * kG>(acc, lane, dacc); }
+      if (diag && self_pairs) { sweep_tile<true, true>(buf, T, oa, ob, lane, acc); flush<15>(acc, lane, dacc); }
+      else if (diag)          { sweep_tile<true>(buf, T, oa, ob, lane, acc); flush<10>(acc, lane, dacc); }
+      else                    { sweep_tile<false>(buf, T, oa, ob, lane, acc); flush<kG * kG>(acc, lane, dacc); }
     }
     __syncthreads();
     cur ^= 1;
@@ -178,11 +197,7 @@ k2_pairdist(const __grid_constant__ RowTable rows, const int n, const int T, con
     int i, j;
     bool valid;
     if (diag) {
-      // lane p -> p-th pair (i < j) of the group, row-major: (0,1..4) (1,2..4) (2,3..4) (3,4)
-      i = (lane >= 9) ? 3 : (lane >= 7) ? 2 : (lane >= 4) ? 1 : 0;
-      const int first = (i == 0) ? 0 : (i == 1) ? 4 : (i == 2) ? 7 : 9;
-      j = lane - first + i + 1;
-      valid = lane < 10;
+      diag_pair(lane, self_pairs != 0, i, j, valid);
     } else {
       i = lane / kG; j = lane % kG;
       valid = lane < kG * kG;
@@ -232,7 +247,7 @@ __device__ __forceinline__ void tma_load_1d(float* dst, const float* src, unsign
 template <int STAGES>
 __global__ void __launch_bounds__(kK2Threads, 1)
 k2_pairdist_tma(const __grid_constant__ RowTable rows, const int n, const int64_t d, const int64_t nfull,
-                double* __restrict__ parts) {
+                const int self_pairs, double* __restrict__ parts) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int T = kTmaT;
   float* stages = reinterpret_cast<float*>(smem_raw);
@@ -289,13 +304,14 @@ k2_pairdist_tma(const __grid_constant__ RowTable rows, const int n, const int64_
     if (active) {
       mbar_wait(&full[s], parity);
       const float* buf = stages + (size_t)s * stage_floats;
-      if (diag) sweep_tile<true>(buf, T, oa, ob, lane, acc);
-      else      sweep_tile<false>(buf, T, oa, ob, lane, acc);
+      if (diag && self_pairs) sweep_tile<true, true>(buf, T, oa, ob, lane, acc);
+      else if (diag)          sweep_tile<true>(buf, T, oa, ob, lane, acc);
+      else                    sweep_tile<false>(buf, T, oa, ob, lane, acc);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
       if (++pending == 2) {          // <= 16 terms per accumulator half between flushes
         pending = 0;
-        if (diag) flush<10>(acc, lane, dacc); else flush<kG * kG>(acc, lane, dacc);
+        if (diag) flush<15>(acc, lane, dacc); else flush<kG * kG>(acc, lane, dacc);
       }
     }
     if (threadIdx.x == 0 && k + STAGES < mine) {
@@ -312,22 +328,20 @@ k2_pairdist_tma(const __grid_constant__ RowTable rows, const int n, const int64_
     cp_async_wait<0>();
     __syncthreads();
     if (active) {
-      if (diag) sweep_tile<true>(stages, T, oa, ob, lane, acc);
-      else      sweep_tile<false>(stages, T, oa, ob, lane, acc);
+      if (diag && self_pairs) sweep_tile<true, true>(stages, T, oa, ob, lane, acc);
+      else if (diag)          sweep_tile<true>(stages, T, oa, ob, lane, acc);
+      else                    sweep_tile<false>(stages, T, oa, ob, lane, acc);
       pending = 1;
     }
   }
   if (active && pending > 0) {
-    if (diag) flush<10>(acc, lane, dacc); else flush<kG * kG>(acc, lane, dacc);
+    if (diag) flush<15>(acc, lane, dacc); else flush<kG * kG>(acc, lane, dacc);
   }
   if (active) {
     int i, j;
     bool valid;
     if (diag) {
-      i = (lane >= 9) ? 3 : (lane >= 7) ? 2 : (lane >= 4) ? 1 : 0;
-      const int first = (i == 0) ? 0 : (i == 1) ? 4 : (i == 2) ? 7 : 9;
-      j = lane - first + i + 1;
-      valid = lane < 10;
+      diag_pair(lane, self_pairs != 0, i, j, valid);
     } else {
       i = lane / kG; j = lane % kG;
       valid = lane < kG * kG;
@@ -372,7 +386,7 @@ static int sm_count() {
 }
 
 template <int STAGES>
-static void launch_tma(const RowTable& rows, int n, int64_t d, int gx, int gy, double* parts, cudaStream_t st) {
+static void launch_tma(const RowTable& rows, int n, int64_t d, int gx, int gy, int self_pairs, double* parts, cudaStream_t st) {
   const size_t smem = (size_t)STAGES * n * kTmaT * sizeof(float) + 2 * STAGES * sizeof(unsigned long long);
   static unsigned long long opted = 0;
   {
@@ -384,10 +398,10 @@ static void launch_tma(const RowTable& rows, int n, int64_t d, int gx, int gy, d
       opted |= bit;
     }
   }
-  k2_pairdist_tma<STAGES><<<dim3(gx, gy), kK2Threads, smem, st>>>(rows, n, d, d / kTmaT, parts);
+  k2_pairdist_tma<STAGES><<<dim3(gx, gy), kK2Threads, smem, st>>>(rows, n, d, d / kTmaT, self_pairs, parts);
 }
 
-int launch_pairdist(const RowTable& rows, int n, int64_t d, double* parts, cudaStream_t st) {
+int launch_pairdist(const RowTable& rows, int n, int64_t d, double* parts, cudaStream_t st, int self_pairs) {
   const int ng = (n + kG - 1) / kG;
   const int ntasks = ng * (ng + 1) / 2;
   const int gy = (ntasks + kK2Warps - 1) / kK2Warps;
@@ -403,9 +417,9 @@ int launch_pairdist(const RowTable& rows, int n, int64_t d, double* parts, cudaS
     if (gx < 1) gx = 1;
     if (gx > kMaxParts) gx = kMaxParts;
     if ((int64_t)gx > ntiles) gx = (int)(ntiles > 0 ? ntiles : 1);
-    if (stages_fit >= 4)      launch_tma<4>(rows, n, d, gx, gy, parts, st);
-    else if (stages_fit == 3) launch_tma<3>(rows, n, d, gx, gy, parts, st);
-    else                      launch_tma<2>(rows, n, d, gx, gy, parts, st);
+    if (stages_fit >= 4)      launch_tma<4>(rows, n, d, gx, gy, self_pairs, parts, st);
+    else if (stages_fit == 3) launch_tma<3>(rows, n, d, gx, gy, self_pairs, parts, st);
+    else                      launch_tma<2>(rows, n, d, gx, gy, self_pairs, parts, st);
     return gx;
   }
   // Generic path: cp.async staging, any alignment.  Largest power-of-two tile whose two stages
@@ -430,7 +444,7 @@ int launch_pairdist(const RowTable& rows, int n, int64_t d, double* parts, cudaS
   if (gx < 1) gx = 1;
   if (gx > kMaxParts) gx = kMaxParts;
   if ((int64_t)gx > ntiles) gx = (int)(ntiles > 0 ? ntiles : 1);
-  k2_pairdist<<<dim3(gx, gy > 0 ? gy : 1), kK2Threads, smem, st>>>(rows, n, T, logq, d, ntiles, parts);
+  k2_pairdist<<<dim3(gx, gy > 0 ? gy : 1), kK2Threads, smem, st>>>(rows, n, T, logq, d, ntiles, self_pairs, parts);
   return gx;
 }
 

@@ -73,6 +73,38 @@ __device__ void block_sum_parts(const Parts& parts, int nparts, int len, int sli
   __syncthreads();
 }
 
+// Aliased rows (the f Byzantine gradients are ONE tensor repeated, attacks/identical.py:86) are
+// detected on the host by pointer equality; the distance pass then runs on the u unique rows only
+// (with the self pairs i == i) and this map expands its u x u table to the n x n one.
+struct RowMap {
+  unsigned char to_unique[kMaxN];
+  int u;          // number of unique rows (u == n: identity, no expansion)
+};
+
+// dist[i][j] = double(fl32(sqrt(sum_k (x_i - x_j)^2))) from the summed u x u table `sq`;
+// diagonal = `diag`.  `sq` and `dist` must not overlap when map.u < n.
+__device__ void finish_distances_mapped(const double* sq, const RowMap& map, int n, bool map_nonfinite, double diag, double* dist) {
+  const int u = map.u;
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e - i * n;
+    if (i < j) {
+      // aliases (a == b) read the diagonal: 0 for a finite row, NaN for a row holding NaN / inf,
+      // exactly what the reference's x.sub(x).norm() gives
+      const int a = map.to_unique[i], b = map.to_unique[j];
+      double v = (double)(float)sqrt(sq[min(a, b) * u + max(a, b)]);
+      if (map_nonfinite && !finite_d(v)) v = CUDART_INF;
+      dist[i * n + j] = v;
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e - i * n;
+    if (i > j) dist[e] = dist[j * n + i];
+    else if (i == j) dist[e] = diag;
+  }
+  __syncthreads();
+}
+
 // dist[i][j] = double(fl32(sqrt(sum_k (x_i - x_j)^2))) from the summed table `sq` (in place
 // allowed); diagonal = `diag`.
 __device__ void finish_distances(const double* sq, int n, bool map_nonfinite, double diag, double* dist) {
@@ -146,15 +178,20 @@ __device__ void stable_order(const double* key, int n, int32_t* __restrict__ ord
 // can only be reached after every finite distance, where the sum is +inf either way.
 template <class Parts>
 __global__ void __launch_bounds__(kK5Threads)
-k5_score_select(const __grid_constant__ Parts parts, int nparts, int n, int count, int32_t* __restrict__ order,
-                int32_t* __restrict__ status, int f, int m, int bulyan, int slices) {
+k5_score_select(const __grid_constant__ Parts parts, const __grid_constant__ RowMap map, int nparts, int n, int count,
+                int32_t* __restrict__ order, int32_t* __restrict__ status, int f, int m, int bulyan, int slices) {
   extern __shared__ double sm[];
   double* dist = sm;
   double* sorted = sm + n * n;
   double* score = sm + 2 * n * n;
   double* scratch = score + n;
-  block_sum_parts(parts, nparts, n * n, slices, scratch, dist);
-  finish_distances(dist, n, true, CUDART_INF, dist);
+  if (map.u == n) {
+    block_sum_parts(parts, nparts, n * n, slices, scratch, dist);
+    finish_distances(dist, n, true, CUDART_INF, dist);
+  } else {
+    block_sum_parts(parts, nparts, map.u * map.u, slices, scratch, sorted);   // u x u table, parked in `sorted`
+    finish_distances_mapped(sorted, map, n, true, CUDART_INF, dist);
+  }
   sort_rows(dist, sorted, n);
   for (int i = threadIdx.x; i < n; i += blockDim.x) score[i] = py_sum(sorted + i * n, count);
   __syncthreads();
@@ -210,8 +247,8 @@ __device__ __forceinline__ unsigned long long sat_add(unsigned long long a, unsi
 
 template <class Parts>
 __global__ void __launch_bounds__(kK5Threads)
-k5_brute_select(const __grid_constant__ Parts parts, int nparts, int n, int f, unsigned long long total,
-                int32_t* __restrict__ sel, int32_t* __restrict__ status, int slices) {
+k5_brute_select(const __grid_constant__ Parts parts, const __grid_constant__ RowMap map, int nparts, int n, int f,
+                unsigned long long total, int32_t* __restrict__ sel, int32_t* __restrict__ status, int slices) {
   extern __shared__ double sm[];
   double* dist = sm;                                                  // n*n
   unsigned long long* binom = reinterpret_cast<unsigned long long*>(sm + n * n);   // (n+1)*(n+1)
@@ -220,8 +257,14 @@ k5_brute_select(const __grid_constant__ Parts parts, int nparts, int n, int f, u
   __shared__ unsigned long long best_rank[kK5Threads / 32];
   const int k = n - f;
   const int W = n + 1;
-  block_sum_parts(parts, nparts, n * n, slices, scratch, dist);
-  finish_distances(dist, n, false, 0., dist);
+  if (map.u == n) {
+    block_sum_parts(parts, nparts, n * n, slices, scratch, dist);
+    finish_distances(dist, n, false, 0., dist);
+  } else {
+    double* table = reinterpret_cast<double*>(binom);        // u x u table, parked where the Pascal triangle goes next
+    block_sum_parts(parts, nparts, map.u * map.u, slices, scratch, table);
+    finish_distances_mapped(table, map, n, false, 0., dist);
+  }
   // Pascal triangle, row by row
   for (int a = 0; a <= n; ++a) {
     for (int b = threadIdx.x; b <= n; b += blockDim.x) {
@@ -338,18 +381,33 @@ static void opt_in_once(K kernel, size_t bytes, unsigned long long& mask) {
 constexpr size_t kScoreSmemMax = (size_t)(2 * kMaxN * kMaxN + kMaxN) * sizeof(double) + 48 * 1024;
 constexpr size_t kBruteSmemMax = (size_t)kMaxN * kMaxN * sizeof(double) + (size_t)(kMaxN + 1) * (kMaxN + 1) * sizeof(unsigned long long) + 48 * 1024;
 
+static RowMap identity_map(int n) {
+  RowMap map;
+  for (int i = 0; i < kMaxN; ++i) map.to_unique[i] = (unsigned char)(i < n ? i : 0);
+  map.u = n;
+  return map;
+}
+
+static RowMap make_map(const int* to_unique, int n, int u) {
+  if (to_unique == nullptr || u >= n) return identity_map(n);
+  RowMap map;
+  for (int i = 0; i < kMaxN; ++i) map.to_unique[i] = (unsigned char)(i < n ? to_unique[i] : 0);
+  map.u = u;
+  return map;
+}
+
 template <class Parts>
-static void score_select(const Parts& parts, int nparts, int n, int count, int32_t* order, int32_t* status, int f, int m,
+static void score_select(const Parts& parts, const RowMap& map, int nparts, int n, int count, int32_t* order, int32_t* status, int f, int m,
                          int bulyan, cudaStream_t st) {
   const int slices = pick_slices(n, nparts);
   const size_t smem = (size_t)(2 * n * n + n + slices * n * n) * sizeof(double);
   static unsigned long long opted = 0;
   opt_in_once(k5_score_select<Parts>, kScoreSmemMax, opted);
-  k5_score_select<Parts><<<1, kK5Threads, smem, st>>>(parts, nparts, n, count, order, status, f, m, bulyan, slices);
+  k5_score_select<Parts><<<1, kK5Threads, smem, st>>>(parts, map, nparts, n, count, order, status, f, m, bulyan, slices);
 }
 
 template <class Parts>
-static int brute_select(const Parts& parts, int nparts, int n, int f, int32_t* sel, int32_t* status, cudaStream_t st) {
+static int brute_select(const Parts& parts, const RowMap& map, int nparts, int n, int f, int32_t* sel, int32_t* status, cudaStream_t st) {
   // C(n, n-f) on the host, saturating
   const int k = n - f;
   unsigned long long total = 1;
@@ -364,7 +422,7 @@ static int brute_select(const Parts& parts, int nparts, int n, int f, int32_t* s
                       (size_t)slices * n * n * sizeof(double);
   static unsigned long long opted = 0;
   opt_in_once(k5_brute_select<Parts>, kBruteSmemMax, opted);
-  k5_brute_select<Parts><<<1, kK5Threads, smem, st>>>(parts, nparts, n, f, total, sel, status, slices);
+  k5_brute_select<Parts><<<1, kK5Threads, smem, st>>>(parts, map, nparts, n, f, total, sel, status, slices);
   return 0;
 }
 
@@ -374,14 +432,18 @@ static PeerParts make_peers(const double* const* ptrs, int npeers) {
   return p;
 }
 
-void launch_krum_select(const double* parts, int nparts, int n, int f, int32_t* order, cudaStream_t st) {
-  score_select(StridedParts{parts, (size_t)n * n}, nparts, n, n - f - 1, order, nullptr, f, 0, 0, st);
+// to_unique / u: optional alias map (see RowMap); the blocks are then u x u tables.
+void launch_krum_select(const double* parts, int nparts, int n, int f, int32_t* order, cudaStream_t st, const int* to_unique, int u) {
+  const RowMap map = make_map(to_unique, n, u);
+  score_select(StridedParts{parts, (size_t)map.u * map.u}, map, nparts, n, n - f - 1, order, nullptr, f, 0, 0, st);
 }
-void launch_bulyan_select(const double* parts, int nparts, int n, int f, int m, int32_t* order, int32_t* status, cudaStream_t st) {
-  score_select(StridedParts{parts, (size_t)n * n}, nparts, n, m, order, status, f, m, 1, st);
+void launch_bulyan_select(const double* parts, int nparts, int n, int f, int m, int32_t* order, int32_t* status, cudaStream_t st, const int* to_unique, int u) {
+  const RowMap map = make_map(to_unique, n, u);
+  score_select(StridedParts{parts, (size_t)map.u * map.u}, map, nparts, n, m, order, status, f, m, 1, st);
 }
-int launch_brute_select(const double* parts, int nparts, int n, int f, int32_t* sel, int32_t* status, cudaStream_t st) {
-  return brute_select(StridedParts{parts, (size_t)n * n}, nparts, n, f, sel, status, st);
+int launch_brute_select(const double* parts, int nparts, int n, int f, int32_t* sel, int32_t* status, cudaStream_t st, const int* to_unique, int u) {
+  const RowMap map = make_map(to_unique, n, u);
+  return brute_select(StridedParts{parts, (size_t)map.u * map.u}, map, nparts, n, f, sel, status, st);
 }
 void launch_rowdist_select(const double* parts, int nparts, int n, int sqrt_norm, int32_t* order, cudaStream_t st) {
   k5_rowdist_select<StridedParts><<<1, kRowSelThreads, 0, st>>>(StridedParts{parts, (size_t)n}, nparts, n, sqrt_norm, order);
@@ -389,13 +451,13 @@ void launch_rowdist_select(const double* parts, int nparts, int n, int sqrt_norm
 
 // Peer variants: block p is read from peers[p] (NVLink peer memory)
 void launch_krum_select_peers(const double* const* peers, int npeers, int n, int f, int32_t* order, cudaStream_t st) {
-  score_select(make_peers(peers, npeers), npeers, n, n - f - 1, order, nullptr, f, 0, 0, st);
+  score_select(make_peers(peers, npeers), identity_map(n), npeers, n, n - f - 1, order, nullptr, f, 0, 0, st);
 }
 void launch_bulyan_select_peers(const double* const* peers, int npeers, int n, int f, int m, int32_t* order, int32_t* status, cudaStream_t st) {
-  score_select(make_peers(peers, npeers), npeers, n, m, order, status, f, m, 1, st);
+  score_select(make_peers(peers, npeers), identity_map(n), npeers, n, m, order, status, f, m, 1, st);
 }
 int launch_brute_select_peers(const double* const* peers, int npeers, int n, int f, int32_t* sel, int32_t* status, cudaStream_t st) {
-  return brute_select(make_peers(peers, npeers), npeers, n, f, sel, status, st);
+  return brute_select(make_peers(peers, npeers), identity_map(n), npeers, n, f, sel, status, st);
 }
 void launch_rowdist_select_peers(const double* const* peers, int npeers, int n, int sqrt_norm, int32_t* order, cudaStream_t st) {
   k5_rowdist_select<PeerParts><<<1, kRowSelThreads, 0, st>>>(make_peers(peers, npeers), npeers, n, sqrt_norm, order);
