@@ -261,8 +261,9 @@ def run_b200(args):
     barrier()
     # keep the sampler alive a little when the region is very short
     # (a FIXED number of extra steps: every rank must issue the same collectives)
-    if total_ms < 50:
-      extra = int(min(2000, max(10, 50.0 / max(total_ms / args.steps, 1e-3))))
+    # NVML queries take tens of milliseconds each: keep the same load running for ~0.4 s more
+    if total_ms < 400:
+      extra = int(min(20000, max(10, 400.0 / max(total_ms / args.steps, 1e-3))))
       if dist is not None:
         count = torch.tensor([extra], device=device, dtype=torch.int64)
         dist.broadcast(count, src=0)
