@@ -51,12 +51,16 @@ def test_phases_compose_to_the_single_device_result(n, nb, f, d, R):
   if n >= 4 * f + 3:
     order_b, status = engine.bulyan_select(parts, n, f, m)
     assert int(status.item()) == 0
+    order_bp, status_p = engine.bulyan_select_peers([b.data_ptr() for b in blocks], n, f, m, full[0].device)
+    assert order_bp.cpu().tolist() == order_b.cpu().tolist() and int(status_p.item()) == 0
     refb, infob = orc.bulyan(np_rows, f, return_info=True)
     got = cat([engine.bulyan_reduce(s, f, m, order_b, status) for s in shards])
     parity.assert_close_scaled(got, refb, parity.column_scale(infob["stage1"]), "bulyan sharded", exempt=infob["ambiguous"])
   # brute (small n only)
   if n <= 11:
     sel, status = engine.brute_select(parts, n, f)
+    sel_p, _ = engine.brute_select_peers([b.data_ptr() for b in blocks], n, f, full[0].device)
+    assert sel_p.cpu().tolist() == sel.cpu().tolist()
     refr, infor = orc.brute(np_rows, f, return_info=True)
     assert int(status.item()) == 0 and [min(i, n - nb) for i in sel.cpu().tolist()] == [min(i, n - nb) for i in infor["selection"]]
     parity.assert_bit_exact(cat([engine.average_selected(s, sel, n - f, status=status) for s in shards]), refr, "brute sharded")
@@ -85,6 +89,27 @@ def test_sharded_aggregate_world_size_one():
   for gar, params in (("median", {}), ("trmean", dict(f=f)), ("krum", dict(f=f)), ("brute", dict(f=f)), ("cge", dict(f=f)), ("aksel", dict(f=f))):
     got = sharded.aggregate(gar, rows, **params).cpu().numpy()
     parity.assert_bit_exact(got, orc.GARS[gar](np_rows, **params), gar)
+
+def test_plan_for_every_rule():
+  import byzantinemomentum_b200 as bz
+  n, nb, f, d = 11, 2, 2, 6007
+  host = _inputs(n, nb, d, 31)
+  np_rows = [r.numpy() for r in host]
+  byz = host[-1].to(DEV)
+  rows = [r.to(DEV) for r in host[:n - nb]] + [byz] * nb
+  for gar, params in (("average", {}), ("median", {}), ("trmean", dict(f=f)), ("phocas", dict(f=f)), ("meamed", dict(f=f)),
+                      ("krum", dict(f=f)), ("bulyan", dict(f=f)), ("brute", dict(f=f)), ("aksel", dict(f=f)), ("cge", dict(f=f))):
+    plan = bz.Plan(gar, rows, **params)
+    got = plan().cpu().numpy()
+    ref = orc.GARS[gar](np_rows, **params)
+    if gar in ("phocas", "meamed", "bulyan"):
+      parity.assert_close_scaled(got, ref, parity.column_scale(np.stack(np_rows)), gar + " plan")
+    else:
+      parity.assert_bit_exact(got, ref, gar + " plan")
+    again = plan().cpu().numpy()
+    assert np.array_equal(got, again, equal_nan=True)      # deterministic, run to run
+    if plan.status is not None:
+      assert int(plan.status.item()) == 0
 
 def test_plan_matches_plain_call_and_tracks_in_place_updates():
   import byzantinemomentum_b200 as bz
