@@ -359,13 +359,15 @@ def sweep(torch, bz, device, peak):
   """ Kernel-level numbers for the other rules / sizes (single GPU; not part of `value`). """
   rows_out = []
   flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=device)
-  plan = [(25, 10, 79_510), (25, 10, 1_310_922), (25, 10, 36_489_290), (11, 5, 79_510), (11, 3, 1_310_922), (51, 12, 4_568_373)]
-  for n, f, d in plan:
+  full = ["average", "median", "trmean", "phocas", "meamed", "krum", "bulyan", "aksel", "cge"]
+  short = ["median", "trmean", "krum", "bulyan"]
+  # every rule at BASELINE.json's shapes, plus the d sweep at n = 25 (metric: "per GAR at n=25, d sweep")
+  plan = [(25, 10, 79_510, full), (25, 10, 1_310_922, full), (25, 10, 36_489_290, full), (11, 5, 79_510, full + ["brute"]),
+          (11, 3, 1_310_922, full + ["brute"]), (51, 12, 4_568_373, full),
+          (25, 10, 1 << 16, short), (25, 10, 431_080, short), (25, 10, 2_384_036, short), (25, 10, 1 << 23, short), (25, 10, 1 << 25, short)]
+  for n, f, d, gars in plan:
     gen = torch.Generator(device=device).manual_seed(5)
     rows = [torch.randn(d, device=device, generator=gen) for _ in range(n)]
-    gars = ["average", "median", "trmean", "phocas", "meamed", "krum", "bulyan", "aksel", "cge"]
-    if n <= 11:
-      gars.append("brute")
     for gar in gars:
       ff = default_f(gar, n, f)
       if gar == "bulyan" and n < 4 * ff + 3:
