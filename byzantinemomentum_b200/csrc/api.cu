@@ -1,6 +1,5 @@
-// api.cu — the C ABI of libbyzagg (include/byzagg.h): argument checks, the split of a
-// [d]-long launch into an aligned vector body plus scalar edges, and the kernel chains of
-// every rule.  No device memory is allocated here and nothing synchronises the host.
+// api.cu — the C ABI of libbyzagg (include/byzagg.h): argument checks, the launch geometry
+// (vector width and alignment shift shared by all rows), and the kernel chains of every rule.  No device memory is allocated here and nothing synchronises the host.
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>

@@ -32,16 +32,4 @@ bool launch_meamed_special(int n, int f, const RowTable& rows, const Geom& g, fl
 void launch_average(const RowTable& rows, const Geom& g, const int32_t* sel, int count,
                     int zero_init, float divisor, const int32_t* status, float* out, cudaStream_t st);
 
-// Opt a kernel into > 48 KB of dynamic shared memory once per device.
-template <class K>
-inline void opt_in_smem(K kernel, size_t bytes, unsigned long long& done_mask) {
-  if (bytes <= 48 * 1024) return;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  const unsigned long long bit = 1ull << (dev & 63);
-  if (done_mask & bit) return;
-  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  done_mask |= bit;
-}
-
 }  // namespace bz
