@@ -82,6 +82,26 @@ def test_trmean_specialised_pairs(n, f):
   host = [x[i].numpy() for i in range(n)]
   parity.assert_bit_exact(_call_coord("trmean", rows, f), orc.trmean(host, f), f"trmean n={n} f={f}")
 
+@pytest.mark.parametrize("n", [11, 25, 51])
+def test_every_compile_time_f_of_the_hot_n(n):
+  """ n = 11, 25, 51 have one trmean / phocas / meamed kernel PER f (pruned network, literal partner
+  indices): run all of them, finite and non-finite columns. """
+  d = 3001
+  x = _rand_rows(n, d, 4242 + n)
+  x[0, ::9] = float("nan")
+  x[1, 3::9] = float("inf")
+  x[n - 1, 6::9] = float("-inf")
+  rows = [x[i].to(DEV) for i in range(n)]
+  host = [x[i].numpy() for i in range(n)]
+  xs = x.numpy()
+  for f in range(1, (n - 1) // 2 + 1):
+    parity.assert_bit_exact(_call_coord("trmean", rows, f), orc.trmean(host, f), f"trmean n={n} f={f}")
+    for name, center in (("phocas", orc.trmean(host, f)), ("meamed", orc.median(host))):
+      got = _call_coord(name, rows, f)
+      ref = orc.GARS[name](host, f)
+      amb = parity.closest_ambiguous(xs, n - f, center)
+      parity.assert_close_scaled(got, ref, parity.column_scale(xs), f"{name} n={n} f={f}", exempt=amb)
+
 @pytest.mark.parametrize("d", [1, 2, 3, 4, 5, 7, 8, 31, 127, 128, 129, 511, 513, 1025])
 def test_ragged_sizes(d):
   n, f = 13, 3
