@@ -392,9 +392,41 @@ def sweep(torch, bz, device, peak):
                              frac=alg / (ms * 1e-3) / 1e9 / peak, read_only_frac=n * d * 4 / (ms * 1e-3) / 1e9 / peak))
       except Exception as err:
         rows_out.append(dict(gar=gar, n=n, f=ff, d=d, error=str(err)[:200]))
+    if (n, d) in ((25, 1_310_922), (25, 36_489_290)):
+      rows_out.append(study_metrics_row(torch, bz, rows, n, d, flush, peak))
     del rows
     torch.cuda.empty_cache()
   return rows_out
+
+def study_metrics_row(torch, bz, rows, n, d, flush, peak):
+  """ `tools.compute_avg_dev_max` (attack.py:846-848): bz_avg_dev_max on the device (CUDA events)
+  and through its public call with the host read (wall clock), beside the reference's operator
+  sequence on the same CUDA tensors (oracle/refcost.py, library kernels, wall clock). """
+  import time
+  from oracle import refcost
+  try:
+    times = []
+    for k in range(10):
+      if n * d * 4 < 4 * L2_BYTES:
+        flush.zero_()
+      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a.record(); bz.engine.avg_dev_max_async(rows); b.record()
+      torch.cuda.synchronize()
+      times.append(a.elapsed_time(b))
+    ms = sorted(times[3:])[len(times[3:]) // 2]
+    def wall(fn):
+      fn(); torch.cuda.synchronize()
+      t0 = time.perf_counter()
+      for _ in range(5):
+        fn()
+      torch.cuda.synchronize()
+      return (time.perf_counter() - t0) / 5 * 1e3
+    alg = (2 * n + 2) * d * 4          # rows twice (average, deviations), avg written once and re-read once
+    return dict(gar="avg_dev_max", n=n, f=0, d=d, ms=ms, params_per_s=d / (ms * 1e-3), gbs=alg / (ms * 1e-3) / 1e9,
+                frac=alg / (ms * 1e-3) / 1e9 / peak, read_only_frac=2 * n * d * 4 / (ms * 1e-3) / 1e9 / peak,
+                call_ms=wall(lambda: bz.compute_avg_dev_max(rows)), torch_cuda_ms=wall(lambda: refcost.study_metrics(rows)))
+  except Exception as err:
+    return dict(gar="avg_dev_max", n=n, f=0, d=d, error=str(err)[:200])
 
 def main():
   ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)

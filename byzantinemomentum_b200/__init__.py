@@ -18,7 +18,7 @@ its absence is an error (no CPU fallback).
 
 from . import _lib, engine, gars as _gars, plugin, sharded
 from .gars import gars, make_gar, register, UserException, last_selection
-from .engine import config, Plan
+from .engine import config, Plan, compute_avg_dev_max
 
-__all__ = ["gars", "make_gar", "register", "UserException", "last_selection", "config", "Plan", "engine", "plugin", "sharded"]
+__all__ = ["gars", "make_gar", "register", "UserException", "last_selection", "config", "Plan", "compute_avg_dev_max", "engine", "plugin", "sharded"]
 __version__ = "0.1.0"

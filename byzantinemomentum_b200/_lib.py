@@ -62,6 +62,7 @@ SIGNATURES = {
   "bz_bulyan_select_peers": (_i, [_c_rows, _i, _i, _i, _i, _vp, _vp, _vp]),
   "bz_brute_select_peers": (_i, [_c_rows, _i, _i, _i, _vp, _vp, _vp]),
   "bz_rowdist_select_peers": (_i, [_c_rows, _i, _i, _i, _vp, _vp]),
+  "bz_avg_dev_max": (_i, [_c_rows, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
   "bz_average_selected": (_i, [_c_rows, _i, _vp, _i, _i, _dbl, _vp, _i64, _vp, _vp]),
   "bz_bulyan_reduce": (_i, [_c_rows, _i, _i, _i, _vp, _vp, _i64, _vp, _vp]),
 }

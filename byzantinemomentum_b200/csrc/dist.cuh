@@ -35,6 +35,9 @@ int launch_pairdist(const RowTable& rows, int n, int64_t d, double* parts, cudaS
 int launch_rowdist(const RowTable& rows, int n, const float* const* host_rows, const float* center, int64_t d,
                    double* parts, cudaStream_t st, int reverse = 0);
 
+// max |x| over x[0..d) -> stats[1] (as a double); `bits` is a device scratch word.
+void launch_absmax(const float* x, int64_t d, unsigned* bits, double* stats, cudaStream_t st);
+
 // Sum `nparts` blocks of `len` doubles in index order into `block` (fixed order: deterministic).
 // pair_n > 0: the block is a pair_n x pair_n table of which only entries i < j are defined; the
 // others are written as 0.

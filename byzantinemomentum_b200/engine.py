@@ -13,6 +13,7 @@ compiled library every entry point raises; there is no CPU fallback.
 """
 
 import ctypes
+import math
 import weakref
 
 import torch
@@ -290,6 +291,42 @@ def cge(gradients, f):
                              ws.data_ptr(), ws.numel(), prep.stream)
   _lib.check(code, "bz_cge")
   return _finish(prep, out), meta[:prep.n]
+
+# ---------------------------------------------------------------------------- #
+# Study metrics on the same stack (tools/pytorch.py:97-125, attack.py:846-848)
+
+def avg_dev_max_async(samples):
+  """ (avg, stats): the average of the rows and a DEVICE fp64 vector [2 + n]:
+  stats[0] = ||avg||^2, stats[1] = max |avg|, stats[2 + i] = ||samples[i] - avg||^2.  No sync. """
+  prep = _prepare_device(samples)
+  avg = torch.empty(prep.d, dtype=torch.float32, device=prep.device)
+  stats = torch.empty(2 + prep.n, dtype=torch.float64, device=prep.device)
+  ws = _workspace(prep.device, prep.stream)
+  with _on(prep.device):
+    code = _lib.lib().bz_avg_dev_max(prep.ptrs, prep.n, prep.d, avg.data_ptr(), stats.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), prep.stream)
+  _lib.check(code, "bz_avg_dev_max")
+  return avg, stats
+
+def compute_avg_dev_max(samples):
+  """ Drop-in for `tools.compute_avg_dev_max(samples)` (tools/pytorch.py:97-125): returns
+  (average gradient or None, norm of the average, norm standard deviation, max |coordinate| of the
+  average).  One device->host read of 2 + n doubles instead of the reference's n + 2 `.item()`s. """
+  n = len(samples)
+  if n == 0:
+    return None, math.nan, math.nan, math.nan                 # :105-106
+  avg, stats = avg_dev_max_async(samples)
+  host = stats.tolist()                                       # the only synchronisation
+  norm_avg = math.sqrt(host[0])
+  norm_max = host[1]
+  if n >= 2:
+    norm_var = 0.
+    for value in host[2:]:                                    # :116-120: same left-to-right sum
+      norm_var += value
+    norm_dev = math.sqrt(norm_var / (n - 1))
+  else:
+    norm_dev = math.nan                                       # :122-123
+  return avg, norm_avg, norm_dev, norm_max
 
 # ---------------------------------------------------------------------------- #
 # Phases of the d-sharded multi-GPU path (device tensors only)

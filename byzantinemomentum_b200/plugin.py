@@ -16,7 +16,7 @@ routes lead there without touching a reference file:
 
 from .gars import gars
 
-__all__ = ["install"]
+__all__ = ["install", "install_tools"]
 
 def install(aggregators, prefix="b200-", override=False, names=None):
   """ Register the CUDA rules in the reference's `aggregators` module.
@@ -42,3 +42,22 @@ def install(aggregators, prefix="b200-", override=False, names=None):
         aggregators.register(target, rule.unchecked, rule.check, upper_bound=rule.upper_bound, influence=rule.influence)
       done.append(target)
   return done
+
+def install_tools(tools):
+  """ Replace `tools.compute_avg_dev_max` (tools/pytorch.py:97, used by attack.py:846-848 for the
+  study metrics) with the CUDA version when the samples live on a GPU.  CPU samples keep the
+  reference's own function: this is a device kernel, not a CPU reimplementation.
+  Args:
+    tools  The imported reference `tools` package
+  Returns:
+    The previous function
+  """
+  from . import engine, _lib
+  stock = tools.compute_avg_dev_max
+  def compute_avg_dev_max(samples):
+    if len(samples) > 0 and samples[0].is_cuda and len(samples) <= _lib.MAX_N:
+      return engine.compute_avg_dev_max(samples)
+    return stock(samples)
+  compute_avg_dev_max.__doc__ = stock.__doc__
+  tools.compute_avg_dev_max = compute_avg_dev_max
+  return stock

@@ -51,7 +51,7 @@ import numpy as np
 __all__ = [
   "average", "median", "trmean", "phocas", "meamed", "krum", "bulyan", "brute", "aksel", "cge",
   "pairwise_distances", "krum_order", "bulyan_order", "brute_selection", "aksel_order", "cge_order",
-  "influence", "closest_mean", "aten_mean_dim0", "as_matrix", "GARS"]
+  "influence", "closest_mean", "aten_mean_dim0", "as_matrix", "GARS", "compute_avg_dev_max"]
 
 F32 = np.float32
 
@@ -418,6 +418,35 @@ def cge(gradients, f, return_info=False, **kwargs):
     return out, dict(selection=picked, order=order, norms=nrm,
                      margin=min(_margin(ss, m), _min_adjacent_gap(ss, m)))
   return out
+
+# ---------------------------------------------------------------------------- #
+# Study metrics
+
+def compute_avg_dev_max(samples):
+  """ tools/pytorch.py:97-125 — (average, norm of the average, norm standard deviation, max
+  absolute coordinate of the average).  The average follows the reference's fp32 op order
+  (clone, add_ in list order, div_); the three scalars are reductions whose fp32 summation order
+  the reference leaves to ATen (`norm`, `dot`), so they are restated in fp64 and compared within
+  the float tolerance. """
+  if len(samples) == 0:
+    return None, math.nan, math.nan, math.nan                              # :105-106
+  g = as_matrix(samples)
+  n = g.shape[0]
+  with np.errstate(all="ignore"):
+    avg = (_seq_sum_rows(g, list(range(n)), zero_init=False) / F32(n)).astype(F32)   # :108-111
+    a64 = avg.astype(np.float64)
+    norm_avg = math.sqrt(float(np.sum(a64 * a64)))                         # :112
+    absa = np.abs(avg)
+    norm_max = float("nan") if np.isnan(absa).any() else float(absa.max()) if absa.size else 0.  # :113
+    if n >= 2:
+      norm_var = 0.
+      for i in range(n):                                                   # :116-119
+        diff = (g[i] - avg).astype(F32).astype(np.float64)
+        norm_var += float(np.sum(diff * diff))
+      norm_dev = math.sqrt(norm_var / (n - 1))                             # :120-121
+    else:
+      norm_dev = math.nan                                                  # :122-123
+  return avg, norm_avg, norm_dev, norm_max
 
 # ---------------------------------------------------------------------------- #
 # Influence (ratio of accepted Byzantine gradients)

@@ -130,6 +130,21 @@ def cge(rows, f, **_):
     total.add_(rows[i])
   return total.div_(m)
 
+def study_metrics(rows):
+  """ The operator sequence of tools/pytorch.py:108-121 (average, norm, abs-max, n sub+dot with
+  one `.item()` each), for timing beside `bz_avg_dev_max`. """
+  mean = rows[0].clone()
+  for row in rows[1:]:
+    mean.add_(row)
+  mean.div_(len(rows))
+  length = mean.norm().item()
+  largest = mean.abs().max().item()
+  spread = 0.
+  for row in rows:
+    delta = row.sub(mean)
+    spread += delta.dot(delta).item()
+  return mean, length, spread, largest
+
 RULES = dict(average=average, median=median, trmean=trmean, phocas=phocas, meamed=meamed,
              krum=krum, bulyan=bulyan, brute=brute, aksel=aksel, cge=cge)
 
