@@ -421,9 +421,9 @@ def study_metrics_row(torch, bz, rows, n, d, flush, peak):
         fn()
       torch.cuda.synchronize()
       return (time.perf_counter() - t0) / 5 * 1e3
-    alg = (2 * n + 2) * d * 4          # rows twice (average, deviations), avg written once and re-read once
+    alg = (n + 1) * d * 4              # one pass: every row read once, the average written once
     return dict(gar="avg_dev_max", n=n, f=0, d=d, ms=ms, params_per_s=d / (ms * 1e-3), gbs=alg / (ms * 1e-3) / 1e9,
-                frac=alg / (ms * 1e-3) / 1e9 / peak, read_only_frac=2 * n * d * 4 / (ms * 1e-3) / 1e9 / peak,
+                frac=alg / (ms * 1e-3) / 1e9 / peak, read_only_frac=n * d * 4 / (ms * 1e-3) / 1e9 / peak,
                 call_ms=wall(lambda: bz.compute_avg_dev_max(rows)), torch_cuda_ms=wall(lambda: refcost.study_metrics(rows)))
   except Exception as err:
     return dict(gar="avg_dev_max", n=n, f=0, d=d, error=str(err)[:200])

@@ -35,8 +35,12 @@ int launch_pairdist(const RowTable& rows, int n, int64_t d, double* parts, cudaS
 int launch_rowdist(const RowTable& rows, int n, const float* const* host_rows, const float* center, int64_t d,
                    double* parts, cudaStream_t st, int reverse = 0);
 
-// max |x| over x[0..d) -> stats[1] (as a double); `bits` is a device scratch word.
-void launch_absmax(const float* x, int64_t d, unsigned* bits, double* stats, cudaStream_t st);
+// ---- K6: study metrics in one pass (k6_study.cu) -------------------------------------------------
+// avg = (rows[0] + rows[1] + ...)/n; stats[0] = sum avg^2, stats[1] = max |avg|,
+// stats[2+i] = sum_k (rows[i][k] - avg[k])^2.  `parts` needs kMaxParts*(n+1) doubles (n >= 2) and
+// `bits`: two device scratch words.
+void launch_study(const RowTable& rows, int n, const float* const* host_rows, int64_t d, float* avg,
+                  double* stats, double* parts, unsigned* bits, cudaStream_t st);
 
 // Sum `nparts` blocks of `len` doubles in index order into `block` (fixed order: deterministic).
 // pair_n > 0: the block is a pair_n x pair_n table of which only entries i < j are defined; the

@@ -103,33 +103,6 @@ k2_rowdist(const __grid_constant__ RowTable rows, const int n, const float* __re
   }
 }
 
-// ---- max |x| of a vector (tools/pytorch.py:113 `grad_avg.abs().max()`) -------------------------
-// Order independent, hence deterministic with an atomic: |x| bit patterns compare like unsigned
-// integers and a NaN pattern is larger than +inf, so a NaN propagates like torch's max().
-__global__ void __launch_bounds__(256)
-k_absmax(const float* __restrict__ x, int64_t d, unsigned* __restrict__ out_bits) {
-  unsigned m = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d; i += (int64_t)gridDim.x * blockDim.x)
-    m = max(m, __float_as_uint(x[i]) & 0x7fffffffu);
-#pragma unroll
-  for (int h = 16; h >= 1; h >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, h));
-  if ((threadIdx.x & 31) == 0 && m != 0) atomicMax(out_bits, m);
-}
-
-// stats[0] = sum of squares of avg (already reduced in stats[0]), stats[1] = max |avg| as a double
-__global__ void k_finish_stats(const unsigned* __restrict__ absmax_bits, double* __restrict__ stats) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) stats[1] = (double)__uint_as_float(*absmax_bits);
-}
-
-void launch_absmax(const float* x, int64_t d, unsigned* bits, double* stats, cudaStream_t st) {
-  cudaMemsetAsync(bits, 0, sizeof(unsigned), st);
-  int64_t blocks = (d + 256 * 8 - 1) / (256 * 8);
-  if (blocks > 1184) blocks = 1184;
-  if (blocks < 1) blocks = 1;
-  k_absmax<<<(unsigned)blocks, 256, 0, st>>>(x, d, bits);
-  k_finish_stats<<<1, 32, 0, st>>>(bits, stats);
-}
-
 static int rd_sm_count() {
   static int cached[64] = {0};
   int dev = 0;

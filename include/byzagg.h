@@ -151,8 +151,8 @@ BZ_API int bz_bulyan_reduce(const float* const* rows, int n, int f, int m, const
 /* ---- Study metrics on the same [n, d] data (tools/pytorch.py:97-125 `compute_avg_dev_max`,
  * called three times per step by attack.py:846-848): avg = (g0 + g1 + ...)/n (clone, add_, div_),
  * stats[0] = sum_k avg[k]^2, stats[1] = max_k |avg[k]|, stats[2+i] = sum_k (g_i[k] - avg[k])^2.
- * avg: device fp32[d]; stats: device double[2+n].  Two passes over the rows instead of n+2 with
- * n host syncs; the caller derives norm_avg = sqrt(stats[0]) and
+ * avg: device fp32[d]; stats: device double[2+n].  One pass over the rows instead of n+2 with
+ * n+2 host syncs; the caller derives norm_avg = sqrt(stats[0]) and
  * norm_dev = sqrt(sum_i stats[2+i] / (n-1)). */
 BZ_API int bz_avg_dev_max(const float* const* rows, int n, int64_t d, float* avg, double* stats,
                           void* ws, size_t ws_bytes, void* stream);
