@@ -18,3 +18,11 @@ PY
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_$tag.csv python bench.py --steps 5 --warmup 3 --no-sweep > gpurun_out/ncu_b_$tag.log 2>&1
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:k1_sorted -s 3 -c 2 -o gpurun_out/prof_trmean_$tag python bench.py --steps 5 --warmup 3 --no-sweep > gpurun_out/ncu_c_$tag.log 2>&1
 ls gpurun_out | tail -4
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:k6_study -c 2 -o gpurun_out/prof_study_$tag python - > gpurun_out/ncu_d_$tag.log 2>&1 <<PY
+import torch, byzantinemomentum_b200 as bz
+rows = [torch.randn(36489290, device="cuda") for _ in range(25)]
+for _ in range(2):
+  bz.engine.avg_dev_max_async(rows)
+torch.cuda.synchronize()
+PY
+ls gpurun_out | tail -4
