@@ -22,10 +22,8 @@ from . import _lib
 
 __all__ = ["average", "median", "trmean", "phocas", "meamed", "krum", "bulyan", "brute", "aksel", "cge",
            "pairdist_partial", "rowdist_partial", "krum_select", "bulyan_select", "brute_select",
-           "rowdist_select", "average_selected", "bulyan_reduce", "config", "DataError", "Plan"]
-
-class DataError(Exception):
-  """ Placeholder base; the concrete errors raised mirror the reference (AssertionError, TypeError). """
+           "rowdist_select", "average_selected", "bulyan_reduce", "avg_dev_max_async", "compute_avg_dev_max",
+           "config", "Plan"]
 
 class _Config:
   """ strict_status: after brute / bulyan, read the device status word (one 4-byte D2H copy,
@@ -298,7 +296,7 @@ def cge(gradients, f):
 def avg_dev_max_async(samples):
   """ (avg, stats): the average of the rows and a DEVICE fp64 vector [2 + n]:
   stats[0] = ||avg||^2, stats[1] = max |avg|, stats[2 + i] = ||samples[i] - avg||^2.  No sync. """
-  prep = _prepare_device(samples)
+  prep = _prepare_device(samples, "the study metrics take CUDA tensors (tools.compute_avg_dev_max handles CPU samples)")
   avg = torch.empty(prep.d, dtype=torch.float32, device=prep.device)
   stats = torch.empty(2 + prep.n, dtype=torch.float64, device=prep.device)
   ws = _workspace(prep.device, prep.stream)
@@ -331,10 +329,10 @@ def compute_avg_dev_max(samples):
 # ---------------------------------------------------------------------------- #
 # Phases of the d-sharded multi-GPU path (device tensors only)
 
-def _prepare_device(gradients):
+def _prepare_device(gradients, message="the sharded phases take CUDA tensors"):
   prep = _prepare(gradients)
   if prep.to_cpu:
-    raise ValueError("the sharded phases take CUDA tensors")
+    raise ValueError(message)
   return prep
 
 def pairdist_partial(gradients):
@@ -499,10 +497,13 @@ class Plan:
     n, d = prep.n, prep.d
     self.gar, self.n, self.d, self.device = gar, n, d, prep.device
     self.rows = list(gradients)
+    if not all(g.is_contiguous() for g in self.rows):
+      # a packed copy would neither stay alive nor follow in-place updates of the originals
+      raise ValueError("Plan takes contiguous rows (the plain call accepts strided views and packs them)")
     self.out = torch.empty(d, dtype=torch.float32, device=prep.device) if out is None else out
     if self.out.dtype != torch.float32 or self.out.shape != (d,) or self.out.device != prep.device or not self.out.is_contiguous():
       raise ValueError("out must be a contiguous float32 vector like the rows")
-    self._ptrs = (ctypes.c_void_p * n)(*[g.data_ptr() for g in (g if g.is_contiguous() else g.contiguous() for g in self.rows)])
+    self._ptrs = (ctypes.c_void_p * n)(*[g.data_ptr() for g in self.rows])
     self._stream = prep.stream
     self.selection = None
     self.status = None
@@ -535,7 +536,11 @@ class Plan:
         raise KeyError(f"unknown aggregation rule {gar!r}")
     self._fn, self._args, self._what = fn, args, "bz_" + gar
   def __call__(self):
-    code = self._fn(*self._args)
+    if torch.cuda.current_device() == self.device.index:
+      code = self._fn(*self._args)
+    else:
+      with _on(self.device):           # the launches go to the device that owns the rows
+        code = self._fn(*self._args)
     if code != 0:
       _lib.check(code, self._what)
     return self.out

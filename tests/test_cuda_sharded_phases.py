@@ -126,3 +126,13 @@ def test_plan_matches_plain_call_and_tracks_in_place_updates():
   ref, info = orc.krum([x[i].numpy() for i in range(n)], 5, return_info=True)
   assert kp.selection.cpu().tolist()[:n - 7] == info["selection"]
   parity.assert_bit_exact(out, ref, "krum plan")
+
+def test_plan_rejects_strided_rows_but_the_plain_call_packs_them():
+  import byzantinemomentum_b200 as bz
+  x = torch.randn(64, 7, generator=torch.Generator().manual_seed(12)).to(DEV)
+  columns = [x[:, i] for i in range(7)]               # 1-D views with stride 7
+  assert not columns[0].is_contiguous()
+  with pytest.raises(ValueError):
+    bz.Plan("median", columns)
+  got = bz.gars["median"].unchecked(gradients=columns)
+  parity.assert_bit_exact(got.cpu().numpy(), orc.median([c.cpu().numpy() for c in columns]), "median of strided views")
