@@ -22,12 +22,14 @@ multi-GPU form of its `aggregate(gradients, f, ...)`.
 phases raise.
 """
 
+import math
+
 import torch
 import torch.distributed as dist
 
 from . import engine as _engine
 
-__all__ = ["aggregate", "aggregate_p2p", "PeerExchange", "COORDINATE_WISE", "DISTANCE_BASED"]
+__all__ = ["aggregate", "aggregate_p2p", "compute_avg_dev_max", "PeerExchange", "COORDINATE_WISE", "DISTANCE_BASED"]
 
 COORDINATE_WISE = ("average", "median", "trmean", "phocas", "meamed")
 DISTANCE_BASED = ("krum", "bulyan", "brute", "aksel", "cge")
@@ -174,3 +176,37 @@ def aggregate(gar, gradients, f=None, m=None, mode="mid", group=None, backend=No
   else:
     raise KeyError(f"unknown aggregation rule {gar!r}")
   return (out, sel) if return_selection else out
+
+def compute_avg_dev_max(samples, group=None, backend=None):
+  """ `tools.compute_avg_dev_max` (tools/pytorch.py:97-125) over d-sharded samples: every rank
+  passes its columns of the n samples and gets its shard of the average plus the GLOBAL scalars.
+  One pass over the local shard (`avg_dev_max_async`), then ONE all-gather of 2 + n doubles; the
+  sums of squares are added in rank order and the maxima compared, so every rank returns
+  bitwise the same three numbers.
+  Returns:
+    (this rank's shard of the average or None, norm of the average, norm standard deviation,
+     max |coordinate| of the average)
+  """
+  be = backend or _engine
+  n = len(samples)
+  if n == 0:
+    return None, math.nan, math.nan, math.nan
+  avg, stats = be.avg_dev_max_async(samples)
+  gathered = _gather(stats, group).tolist()            # [R][2 + n]; the only synchronisation
+  norm_sq, norm_max, norm_var = 0., 0., 0.
+  for rank_stats in gathered:                          # rank order
+    norm_sq += rank_stats[0]
+    if math.isnan(rank_stats[1]) or math.isnan(norm_max):
+      norm_max = math.nan                              # torch's max propagates a NaN; Python's max() may drop it
+    elif rank_stats[1] > norm_max:
+      norm_max = rank_stats[1]
+  if n >= 2:
+    for i in range(n):                                 # sample order, ranks inside
+      dev = 0.
+      for rank_stats in gathered:
+        dev += rank_stats[2 + i]
+      norm_var += dev
+    norm_dev = math.sqrt(norm_var / (n - 1))
+  else:
+    norm_dev = math.nan
+  return avg, math.sqrt(norm_sq), norm_dev, norm_max

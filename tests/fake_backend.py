@@ -105,3 +105,16 @@ class OracleBackend:
     sel = orc.bulyan_stage1(g, [int(i) for i in order], f, m)
     theta = sel.shape[0]
     return _t(orc.closest_mean(sel, theta - 2 * f, orc.median(sel)))
+
+  # study metrics
+  def avg_dev_max_async(self, rows):
+    g = orc.as_matrix(_np(rows))
+    avg = orc.compute_avg_dev_max(list(g))[0]
+    with np.errstate(all="ignore"):
+      a64 = avg.astype(np.float64)
+      absa = np.abs(avg)
+      stats = [float(np.sum(a64 * a64)), float("nan") if np.isnan(absa).any() else float(absa.max())]
+      for i in range(g.shape[0]):
+        diff = (g[i] - avg).astype(np.float32).astype(np.float64)
+        stats.append(float(np.sum(diff * diff)))
+    return _t(avg), _t(np.array(stats, dtype=np.float64))

@@ -44,6 +44,17 @@ def _worker(rank, world, port, queue):
     for i, (gar, params) in enumerate(CASES):
       res, sel = sharded.aggregate(gar, shard, backend=OracleBackend(), return_selection=True, **params)
       out[i] = (res.numpy().copy(), None if sel is None else sel.numpy().copy())
+    study = {}
+    for tag, samples in (("all", shard), ("one", shard[:1]), ("none", [])):
+      avg, norm_avg, norm_dev, norm_max = sharded.compute_avg_dev_max(samples, backend=OracleBackend())
+      study[tag] = (None if avg is None else avg.numpy().copy(), norm_avg, norm_dev, norm_max)
+    if rank == 1:                                       # a NaN on one rank only must reach every rank
+      poisoned = [r.clone() for r in shard]
+      poisoned[2][5] = float("nan")
+    else:
+      poisoned = shard
+    study["nan"] = sharded.compute_avg_dev_max(poisoned, backend=OracleBackend())[1:]
+    out["study"] = study
     queue.put((rank, lo, hi, out))
   finally:
     dist.destroy_process_group()
@@ -76,3 +87,22 @@ def test_two_rank_sharding_matches_single_process():
       parity.assert_bit_exact(full, ref, f"{gar} sharded")
     if sels[0] is not None:
       assert np.array_equal(sels[0], sels[1]), f"{gar}: ranks derived different selections"
+
+  # study metrics: shards of the average concatenate to the oracle's, scalars agree on every rank
+  import math
+  for tag, samples in (("all", rows), ("one", rows[:1]), ("none", [])):
+    ref_avg, ref_norm, ref_dev, ref_max = orc.compute_avg_dev_max(samples)
+    per_rank = [g[3]["study"][tag] for g in got]
+    if ref_avg is None:
+      assert all(r[0] is None for r in per_rank)
+    else:
+      parity.assert_bit_exact(np.concatenate([r[0] for r in per_rank]), ref_avg, f"sharded average ({tag})")
+    assert per_rank[0][1:] == per_rank[1][1:] or all(math.isnan(a) and math.isnan(b) for a, b in zip(per_rank[0][1:], per_rank[1][1:]) if a != b)
+    for got_value, ref_value in zip(per_rank[0][1:], (ref_norm, ref_dev, ref_max)):
+      if math.isnan(ref_value):
+        assert math.isnan(got_value)
+      else:
+        assert abs(got_value - ref_value) <= 1e-12 * abs(ref_value)
+  for r in (0, 1):
+    norm_avg, norm_dev, norm_max = got[r][3]["study"]["nan"]
+    assert math.isnan(norm_avg) and math.isnan(norm_dev) and math.isnan(norm_max)
