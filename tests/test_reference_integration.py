@@ -60,6 +60,13 @@ res.append(same)
 # override: --gar krum now resolves to the CUDA rule
 bz.plugin.install(aggregators, override=True, names=["krum"])
 res.append(aggregators.gars["krum"].unchecked.__module__.startswith("byzantinemomentum_b200"))
+# study metrics: the swap keeps the reference's function for CPU samples, same results
+stock = tools.compute_avg_dev_max
+before = stock([torch.arange(6.), torch.ones(6)])
+previous = bz.plugin.install_tools(tools)
+after = tools.compute_avg_dev_max([torch.arange(6.), torch.ones(6)])
+res.append(previous is stock and tools.compute_avg_dev_max is not stock and torch.equal(before[0], after[0]) and before[1:] == after[1:]
+           and tools.compute_avg_dev_max([])[0] is None)
 out.write("RESULT " + " ".join(str(int(x)) for x in res) + "\n")
 out.flush()
 """
@@ -71,4 +78,4 @@ def test_rules_register_inside_the_unmodified_reference(tmp_path):
   proc = subprocess.run([sys.executable, str(script)], cwd=tmp_path, capture_output=True, text=True, timeout=300)
   lines = [l for l in proc.stdout.splitlines() if l.startswith("RESULT")]
   assert lines, proc.stdout[-2000:] + proc.stderr[-2000:]
-  assert lines[-1] == "RESULT 1 1 1 1 1 1 1", proc.stdout[-3000:]
+  assert lines[-1] == "RESULT 1 1 1 1 1 1 1 1", proc.stdout[-3000:]
