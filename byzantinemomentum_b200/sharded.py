@@ -29,7 +29,7 @@ import torch.distributed as dist
 
 from . import engine as _engine
 
-__all__ = ["aggregate", "aggregate_p2p", "compute_avg_dev_max", "PeerExchange", "COORDINATE_WISE", "DISTANCE_BASED"]
+__all__ = ["aggregate", "aggregate_p2p", "compute_avg_dev_max", "replicate", "PeerExchange", "COORDINATE_WISE", "DISTANCE_BASED"]
 
 COORDINATE_WISE = ("average", "median", "trmean", "phocas", "meamed")
 DISTANCE_BASED = ("krum", "bulyan", "brute", "aksel", "cge")
@@ -210,3 +210,30 @@ def compute_avg_dev_max(samples, group=None, backend=None):
   else:
     norm_dev = math.nan
   return avg, math.sqrt(norm_sq), norm_dev, norm_max
+
+def replicate(shard, group=None):
+  """ All-gather the ranks' output shards into the full aggregated gradient on every rank
+  (what a trainer that keeps a replicated model needs before
+  `model.set_gradient`, experiments/model.py:368-380).  Shards may differ in length (the last
+  rank's is shorter when R does not divide d): lengths are exchanged first, shards padded to
+  the longest for the collective and trimmed after it.
+  Args:
+    shard  This rank's [d_r] slice of the result
+    group  Process group (default: the world)
+  Returns:
+    [sum of d_r] vector, the shards in rank order
+  """
+  world = dist.get_world_size(group) if dist.is_initialized() else 1
+  if world == 1:
+    return shard.clone()
+  length = torch.tensor([shard.numel()], dtype=torch.int64, device=shard.device)
+  lengths = torch.empty(world, dtype=torch.int64, device=shard.device)
+  dist.all_gather_into_tensor(lengths, length, group=group)
+  lengths = lengths.tolist()
+  longest = max(lengths)
+  padded = shard if shard.numel() == longest else torch.cat([shard, shard.new_zeros(longest - shard.numel())])
+  gathered = torch.empty(world * longest, dtype=shard.dtype, device=shard.device)
+  dist.all_gather_into_tensor(gathered, padded.contiguous(), group=group)
+  if all(l == longest for l in lengths):
+    return gathered
+  return torch.cat([gathered[r * longest:r * longest + lengths[r]] for r in range(world)])

@@ -55,6 +55,7 @@ def _worker(rank, world, port, queue):
       poisoned = shard
     study["nan"] = sharded.compute_avg_dev_max(poisoned, backend=OracleBackend())[1:]
     out["study"] = study
+    out["replicated"] = sharded.replicate(sharded.aggregate("trmean", shard, f=3, backend=OracleBackend())).numpy().copy()
     queue.put((rank, lo, hi, out))
   finally:
     dist.destroy_process_group()
@@ -106,3 +107,6 @@ def test_two_rank_sharding_matches_single_process():
   for r in (0, 1):
     norm_avg, norm_dev, norm_max = got[r][3]["study"]["nan"]
     assert math.isnan(norm_avg) and math.isnan(norm_dev) and math.isnan(norm_max)
+  # replicated output: every rank ends with the full vector (shards of 301 and 300 columns)
+  for r in (0, 1):
+    parity.assert_bit_exact(got[r][3]["replicated"], orc.trmean(rows, 3), f"replicated output on rank {r}")
