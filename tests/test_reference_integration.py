@@ -79,3 +79,32 @@ def test_rules_register_inside_the_unmodified_reference(tmp_path):
   lines = [l for l in proc.stdout.splitlines() if l.startswith("RESULT")]
   assert lines, proc.stdout[-2000:] + proc.stderr[-2000:]
   assert lines[-1] == "RESULT 1 1 1 1 1 1 1 1", proc.stdout[-3000:]
+
+ATTACK_ARGS = ["--nb-workers", "7", "--nb-decl-byz", "1", "--nb-real-byz", "1", "--attack", "empire", "--attack-args", "factor:1.1",
+               "--model", "simples-full", "--nb-steps", "2", "--device", "cpu", "--batch-size", "8", "--evaluation-delta", "0",
+               "--nb-for-study", "7", "--nb-for-study-past", "2"]
+
+def _drive(tmp_path, gar):
+  cmd = [sys.executable, str(ROOT / "tools" / "drive_attack.py"), "--reference", str(REF), "--shape", "mnist", "--install-tools",
+         "--", "--gar", gar] + ATTACK_ARGS
+  return subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=600)
+
+@pytest.mark.skipif(not (REF / "attack.py").exists(), reason="reference not present on this box")
+def test_unmodified_attack_py_runs_offline_with_the_rules_registered(tmp_path):
+  """ the runpy recipe.  The stock rule drives two full steps (synthetic data,
+  study metrics through the swapped `compute_avg_dev_max`), with every b200-<name> registered. """
+  proc = _drive(tmp_path, "krum")
+  assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
+  assert "registered: b200-average" in proc.stdout and "b200-cge" in proc.stdout
+  assert "Training..." in proc.stdout
+
+@pytest.mark.skipif(not (REF / "attack.py").exists(), reason="reference not present on this box")
+def test_cuda_rule_inside_attack_py_fails_loudly_without_a_gpu(tmp_path):
+  """ No CPU fallback: selecting a CUDA rule on a box without a GPU stops attack.py with the
+  library's error instead of silently computing on the host. """
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip("this box has a GPU")
+  proc = _drive(tmp_path, "b200-krum")
+  assert proc.returncode != 0
+  assert "no CUDA device available" in proc.stdout + proc.stderr
