@@ -28,7 +28,12 @@
 
 namespace bz {
 
-constexpr int kK1Threads = 128;
+// Threads per CTA (A/B builds: `make VARIANT=t64 EXTRA=-DBZ_K1_THREADS=64`; shorter CTAs shrink the
+// ragged last wave at d ~ 1M, at the price of more CTA launches).
+#ifndef BZ_K1_THREADS
+#define BZ_K1_THREADS 128
+#endif
+constexpr int kK1Threads = BZ_K1_THREADS;
 
 // How a thread walks the coordinates (A/B builds: `make VARIANT=v0 EXTRA=-DBZ_K1_VARIANT=0`):
 //   2 (default)  one logical vector per thread, direct register loads, grid = all tiles.  The
@@ -106,11 +111,11 @@ __device__ __forceinline__ void k1_walk(const RowTable& rows, const Geom& g, flo
 
 // ---- median ---------------------------------------------------------------------------
 
-// Register cap: 4 resident CTAs per SM (<= 128 registers) whenever the N x VEC values leave room.
+// Register cap: 512 resident threads per SM (<= 128 registers) whenever the N x VEC values leave room.
 #ifndef BZ_K1_CAP
 #define BZ_K1_CAP 104
 #endif
-__host__ __device__ constexpr int k1_min_blocks(int n, int vec) { return (n * vec <= BZ_K1_CAP) ? 4 : 1; }
+__host__ __device__ constexpr int k1_min_blocks(int n, int vec) { return (n * vec <= BZ_K1_CAP) ? 512 / kK1Threads : 1; }
 
 template <int N, int VEC>
 __global__ void __launch_bounds__(kK1Threads, k1_min_blocks(N, VEC))
