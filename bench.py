@@ -304,7 +304,10 @@ def run_b200(args):
   # ---- end to end through the reference-facing call with HOST buffers ---------------------------
   e2e_steps = max(3, min(args.steps, 20))
   host_sets = 2
-  host = [[torch.randn(d, generator=torch.Generator().manual_seed(99 + 7 * s + r)).pin_memory() for r in range(n)] for s in range(host_sets)]
+  # pinned host buffers, allocated while bound to the GPU-local CPUs (first touch puts the pages on
+  # the GPU's NUMA node: a copy from the other socket runs at a fraction of the PCIe rate)
+  with bz.hostmem.gpu_local_cpus(device.index) as numa_local:
+    host = [[torch.randn(d, generator=torch.Generator().manual_seed(99 + 7 * s + r)).pin_memory() for r in range(n)] for s in range(host_sets)]
   def e2e_step(k):
     out = bz.gars[gar].unchecked(gradients=host[k % host_sets], f=f)
     assert out.device.type == "cpu"
@@ -319,7 +322,7 @@ def run_b200(args):
     e2e_total = float(t.item())
   e2e_ms = e2e_total / e2e_steps
   e2e = dict(value=world * d / (e2e_ms * 1e-3), unit="params/s", h2d_bytes_per_step=n * d * 4, d2h_bytes_per_step=d * 4,
-             ms_per_step=e2e_ms, steps=e2e_steps, call=f"byzantinemomentum_b200.gars[{gar!r}].unchecked(gradients=<{n} pinned host tensors>, f={f})")
+             ms_per_step=e2e_ms, steps=e2e_steps, host_buffers="pinned" + (", allocated on the GPU-local NUMA node" if numa_local else ""), call=f"byzantinemomentum_b200.gars[{gar!r}].unchecked(gradients=<{n} pinned host tensors>, f={f})")
   del host
 
   line = dict(metric="aggregated-params/sec", value=value, unit="params/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),

@@ -16,9 +16,9 @@ Importing this package never touches CUDA; the compiled library is loaded on fir
 its absence is an error (no CPU fallback).
 """
 
-from . import _lib, engine, gars as _gars, plugin, sharded
+from . import _lib, engine, gars as _gars, hostmem, plugin, sharded
 from .gars import gars, make_gar, register, UserException, last_selection
 from .engine import config, Plan, compute_avg_dev_max
 
-__all__ = ["gars", "make_gar", "register", "UserException", "last_selection", "config", "Plan", "compute_avg_dev_max", "engine", "plugin", "sharded"]
+__all__ = ["gars", "make_gar", "register", "UserException", "last_selection", "config", "Plan", "compute_avg_dev_max", "engine", "hostmem", "plugin", "sharded"]
 __version__ = "0.1.0"

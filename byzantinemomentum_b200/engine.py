@@ -18,7 +18,7 @@ import weakref
 
 import torch
 
-from . import _lib
+from . import _lib, hostmem
 
 __all__ = ["average", "median", "trmean", "phocas", "meamed", "krum", "bulyan", "brute", "aksel", "cge",
            "pairdist_partial", "rowdist_partial", "krum_select", "bulyan_select", "brute_select",
@@ -181,7 +181,8 @@ def _finish(prep, out):
   pinned = _host_out.get(key)
   if pinned is None:
     _host_out.clear()
-    pinned = torch.empty(prep.d, dtype=torch.float32, pin_memory=True)
+    with hostmem.gpu_local_cpus(prep.device.index):         # pages on the GPU's NUMA node
+      pinned = torch.empty(prep.d, dtype=torch.float32, pin_memory=True)
     _host_out[key] = pinned
   pinned.copy_(out, non_blocking=True)
   torch.cuda.current_stream(prep.device).synchronize()
