@@ -216,8 +216,19 @@ k2_pairdist(const __grid_constant__ RowTable rows, const int n, const int T, con
 // of the issue slots).  Needs 16-byte aligned rows; the ragged tail tile (and unaligned rows)
 // take the cooperative path.  The producer is lane 0 of warp 0, whose own task is a diagonal
 // (light) one, so waiting for the slowest warp before re-arming a stage costs it nothing.
-constexpr int kTmaT = 512;          // coordinates per tile
-constexpr int kTmaLogQ = 7;         // log2(kTmaT / 4)
+// Tile width and minimum ring depth are build parameters for A/B runs (the bulk-copy issue loop is
+// the measured bottleneck: `make VARIANT=t1024 EXTRA="-DBZ_K2_TMA_T=1024 -DBZ_K2_TMA_MIN_STAGES=2"`
+// halves the copies per coordinate at n = 25).
+#ifndef BZ_K2_TMA_T
+#define BZ_K2_TMA_T 512
+#endif
+#ifndef BZ_K2_TMA_MIN_STAGES
+#define BZ_K2_TMA_MIN_STAGES 3
+#endif
+constexpr int kTmaT = BZ_K2_TMA_T;  // coordinates per tile (a power of two, 256...1024)
+constexpr int kTmaLogQ = (kTmaT == 256) ? 6 : (kTmaT == 512) ? 7 : 8;   // log2(kTmaT / 4)
+constexpr int kTmaFlush = 1024 / kTmaT;   // tiles between flushes: <= 16 terms per accumulator half
+static_assert(kTmaT == 256 || kTmaT == 512 || kTmaT == 1024, "BZ_K2_TMA_T");
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
@@ -309,7 +320,7 @@ k2_pairdist_tma(const __grid_constant__ RowTable rows, const int n, const int64_
       else                    sweep_tile<false>(buf, T, oa, ob, lane, acc);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
-      if (++pending == 2) {          // <= 16 terms per accumulator half between flushes
+      if (++pending == kTmaFlush) {  // <= 16 terms per accumulator half between flushes
         pending = 0;
         if (diag) flush<15>(acc, lane, dacc); else flush<kG * kG>(acc, lane, dacc);
       }
@@ -411,7 +422,7 @@ int launch_pairdist(const RowTable& rows, int n, int64_t d, double* parts, cudaS
   const size_t stage_bytes = (size_t)n * kTmaT * sizeof(float);
   const int stages_fit = (int)((kK2SmemBudget - 256) / stage_bytes);
   static const bool force_generic = getenv("BYZAGG_K2_GENERIC") != nullptr;
-  if (aligned && stages_fit >= 3 && !force_generic) {   // with 2 stages the cp.async path measured faster (n > 36)
+  if (aligned && stages_fit >= BZ_K2_TMA_MIN_STAGES && !force_generic) {   // with 2 stages the cp.async path measured faster (n > 36)
     const int64_t ntiles = (d + kTmaT - 1) / kTmaT;
     int gx = sm_count() / (gy > 0 ? gy : 1);
     if (gx < 1) gx = 1;
