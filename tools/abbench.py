@@ -36,8 +36,12 @@ print("RESULT " + json.dumps(out))
 """ % str(ROOT)
 
 def main():
-  libs = sys.argv[1:]
-  cases = [("average", 25, 10, 1310922), ("median", 25, 10, 1310922), ("trmean", 25, 10, 1310922), ("trmean", 25, 7, 1310922),
+  libs = [a for a in sys.argv[1:] if not a.startswith("--")]
+  if "--dist" in sys.argv:      # the distance-based rules (K2 experiments)
+    cases = [("krum", 25, 5, 1310922), ("bulyan", 25, 5, 1310922), ("krum", 11, 3, 1310922), ("krum", 25, 5, 36489290),
+             ("krum", 36, 8, 4568373), ("krum", 18, 4, 1310922), ("cge", 25, 5, 1310922)]
+  else:
+   cases = [("average", 25, 10, 1310922), ("median", 25, 10, 1310922), ("trmean", 25, 10, 1310922), ("trmean", 25, 7, 1310922),
            ("median", 25, 10, 36489290), ("trmean", 25, 10, 36489290), ("trmean", 25, 7, 36489290),
            ("median", 51, 12, 4568373), ("trmean", 51, 12, 4568373), ("median", 11, 5, 1310922), ("phocas", 25, 10, 1310922)]
   results = {}
