@@ -227,7 +227,12 @@ k2_pairdist(const __grid_constant__ RowTable rows, const int n, const int T, con
 #endif
 constexpr int kTmaT = BZ_K2_TMA_T;  // coordinates per tile (a power of two, 256...1024)
 constexpr int kTmaLogQ = (kTmaT == 256) ? 6 : (kTmaT == 512) ? 7 : 8;   // log2(kTmaT / 4)
-constexpr int kTmaFlush = 1024 / kTmaT;   // tiles between flushes: <= 16 terms per accumulator half
+// BZ_K2_FLUSH_SCALE (A/B builds): 2 = 32 fp32 terms per accumulator half between two flushes into
+// fp64 instead of 16 (the transposed reduction is ~14 % of the executed instructions at n = 25).
+#ifndef BZ_K2_FLUSH_SCALE
+#define BZ_K2_FLUSH_SCALE 1
+#endif
+constexpr int kTmaFlush = (1024 / kTmaT) * BZ_K2_FLUSH_SCALE;   // tiles between flushes: <= 16 terms per accumulator half
 static_assert(kTmaT == 256 || kTmaT == 512 || kTmaT == 1024, "BZ_K2_TMA_T");
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -240,7 +245,20 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// BZ_MBAR_HINT_NS (A/B builds): suspend-time hint of try_wait.  Without it the hardware wait is
+// short and a waiting warp re-issues the probe ~28 times per tile (ncu, n = 25: SYNCS + BRA + YIELD
+// = 11 % of the executed instructions, on the schedulers the working warps need).
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+#ifdef BZ_MBAR_HINT_NS
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity), "r"((unsigned)BZ_MBAR_HINT_NS) : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
@@ -249,6 +267,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}"
       ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_load_1d(float* dst, const float* src, unsigned bytes, unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
