@@ -19,9 +19,10 @@ One JSON line is printed by rank 0 (see the driver contract in the task statemen
               HBM peak of MEASURED_PEAKS.json
   e2e         the same metric through the reference-facing call `gars[gar](gradients=<host
               tensors>, f=f)`: pinned host rows -> H2D -> kernel -> D2H of the result, per step
-  cpu_baseline  the reference's ATen operator sequence (oracle/refcost.py) on the host cores
+  cpu_baseline  the UNMODIFIED reference's `aggregators.gars[gar].unchecked` on CPU tensors, on the host
+                cores (baseline/_ref; the port oracle/refcost.py only when no reference is present)
   sweep       (N=1) kernel time / GB/s / roofline fraction of the other rules and sizes
-`--impl reference` times the CPU operator sequence alone, on the same workload.
+`--impl reference` times the reference's CPU aggregation alone, on the same workload.
 """
 
 import argparse
@@ -161,44 +162,78 @@ def recorded_traffic(gar, n, f, d):
   except Exception:
     return None
 
-def cpu_reference(torch, gar, n, f, d, seed, budget_s, repeats):
-  """ oracle/refcost.py on the host cores, bounded: shrinks d so that `repeats` calls fit `budget_s`. """
+def cpu_info():
+  model = "unknown"
+  try:
+    for line in pathlib.Path("/proc/cpuinfo").read_text().splitlines():
+      if line.startswith("model name"):
+        model = line.split(":", 1)[1].strip()
+        break
+  except OSError:
+    pass
+  try:
+    allowed = len(os.sched_getaffinity(0))
+  except AttributeError:
+    allowed = os.cpu_count() or 1
+  return dict(cpu_model=model, cpus_online=os.cpu_count() or 1, cpus_allowed=allowed)
+
+def reference_callable(gar):
+  """ (fn(rows, f), kind, path): the UNMODIFIED reference's `aggregators.gars[gar].unchecked`
+  (search order $BYZ_REFERENCE, baseline/_ref, /root/reference) — nothing of this
+  repository is on that path — or, only when no reference checkout is present, the port of its
+  ATen operator sequence (oracle/refcost.py). """
+  from oracle import reference
+  root, aggregators = reference.load()
+  if aggregators is not None and gar in aggregators.gars:
+    rule = aggregators.gars[gar].unchecked
+    return (lambda rows, f: rule(gradients=rows, f=f)), "reference", f"{reference.describe()}: aggregators.gars[{gar!r}].unchecked(gradients=<cpu rows>, f=f)"
   from oracle import refcost
+  return (lambda rows, f: refcost.run(gar, rows, f=f)), "port", "oracle/refcost.py: the reference's ATen operator sequence on CPU tensors (no reference checkout found)"
+
+def cpu_reference(torch, gar, n, f, d, seed, budget_s, repeats):
+  """ The reference's CPU aggregation on the host cores, bounded: shrinks d so that `repeats`
+  calls fit `budget_s`. """
+  run, kind, path = reference_callable(gar)
   gen = torch.Generator().manual_seed(seed)
   probe_d = min(d, 65536)
   rows = [torch.randn(probe_d, generator=gen) for _ in range(n)]
   # "all the host threads it can use": os.cpu_count() may exceed what the container is allowed to
   # run, which makes ATen's parallel loops thrash; probe a few thread counts, keep the fastest
-  try:
-    allowed = len(os.sched_getaffinity(0))
-  except AttributeError:
-    allowed = os.cpu_count() or 1
+  info = cpu_info()
+  allowed = info["cpus_allowed"]
   candidates = sorted({torch.get_num_threads(), allowed, os.cpu_count() or 1, 8, 16, 32} & set(range(1, allowed + 1)) | {min(allowed, 8)})
   best_threads, per_elem = None, None
   for threads in candidates:
     torch.set_num_threads(threads)
-    refcost.run(gar, rows, f=f)
+    run(rows, f)
     t0 = time.perf_counter()
-    refcost.run(gar, rows, f=f)
+    run(rows, f)
     cost = (time.perf_counter() - t0) / probe_d
     if per_elem is None or cost < per_elem:
       best_threads, per_elem = threads, cost
   torch.set_num_threads(best_threads)
   sample_d = int(min(d, max(4096, budget_s / max(repeats, 1) / max(per_elem, 1e-12))))
   rows = [torch.randn(sample_d, generator=gen) for _ in range(n)]
-  refcost.run(gar, rows, f=f)  # warm
+  run(rows, f)  # warm
   times = []
   for _ in range(repeats):
     t0 = time.perf_counter()
-    refcost.run(gar, rows, f=f)
+    run(rows, f)
     times.append(time.perf_counter() - t0)
-  return dict(times=times, sample_d=sample_d, threads=torch.get_num_threads())
+  return dict(times=times, sample_d=sample_d, threads=torch.get_num_threads(), kind=kind, path=path, torch=torch.__version__, **info)
+
+def make_config(gar, n, f, d, world):
+  """ The workload description, identical in both arms (the driver compares the dicts). """
+  return dict(workload=f"{gar} GAR, n={n} f={f}, d={d} per GPU (BASELINE.json configs[1]: CIFAR-10 empire-cnn shape)",
+              gar=gar, n=n, f=f, d=d, parallelism=f"d-sharded x{world}" if world > 1 else "single GPU",
+              l2="GPU arm: inputs rotate over independent [n, d] stacks totalling more than 3x the 126 MB L2; CPU arm: not applicable")
 
 # ---------------------------------------------------------------------------- #
 
 def run_reference(args):
   import torch
   rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
   if rank != 0:
     return
   f = default_f(args.gar, args.n, args.f)
@@ -209,9 +244,9 @@ def run_reference(args):
   sample = f"{args.gar} n={args.n} f={f} on d={res['sample_d']} of {args.d} columns per step, {len(times)} timed steps"
   line = dict(impl="reference", metric="aggregated-params/sec", value=value, unit="params/s", n_gpus=args.gpus, steps=len(times),
               warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-              config=dict(workload=f"{args.gar} GAR, n={args.n} f={f}, d={args.d} (BASELINE.json configs[1] shape)", gar=args.gar, n=args.n,
-                          f=f, d=args.d, path="oracle/refcost.py: the reference's ATen operator sequence on CPU tensors"),
-              cpu_baseline=dict(value=value, unit="params/s", cores=res["threads"], kind="port", sample=sample),
+              config=make_config(args.gar, args.n, f, args.d, world),
+              cpu_baseline=dict(value=value, unit="params/s", cores=res["threads"], kind=res["kind"], sample=sample, path=res["path"],
+                                cpu_model=res["cpu_model"], cpus_allowed=res["cpus_allowed"], torch=res["torch"]),
               e2e=dict(value=value, unit="params/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
   print(json.dumps(line), flush=True)
 
@@ -327,17 +362,17 @@ def run_b200(args):
 
   line = dict(metric="aggregated-params/sec", value=value, unit="params/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
               ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-              config=dict(workload=f"{gar} GAR, n={n} f={f}, d={d} per GPU (BASELINE.json configs[1]: CIFAR-10 empire-cnn shape)",
-                          gar=gar, n=n, f=f, d=d, parallelism=f"d-sharded x{world}" if world > 1 else "single GPU", api=api,
-                          plugin_call_ms_per_step=plugin_ms,
-                          l2="inputs rotate over %d independent [n, d] stacks (%.0f MB > L2)" % (sets, sets * set_bytes / 1e6)),
+              config=make_config(gar, n, f, d, world),
+              details=dict(api=api, plugin_call_ms_per_step=plugin_ms,
+                           l2="inputs rotate over %d independent [n, d] stacks (%.0f MB > L2)" % (sets, sets * set_bytes / 1e6)),
               roofline=roofline, e2e=e2e, gpu_launches=args.steps * LAUNCHES[gar], clocks=clocks.summary())
   if rank == 0 and world == 1:
     # ---- CPU baseline: the reference's operator sequence on the host cores (bounded sample) --------
     res = cpu_reference(torch, gar, n, f, d, 4321, budget_s=20.0, repeats=3)
     best = min(res["times"])
-    line["cpu_baseline"] = dict(value=res["sample_d"] / best, unit="params/s", cores=res["threads"], kind="port",
-                                sample=f"best of 3 calls of oracle/refcost.py ({gar}, n={n}, f={f}) on d={res['sample_d']} columns", ms_per_call=best * 1e3)
+    line["cpu_baseline"] = dict(value=res["sample_d"] / best, unit="params/s", cores=res["threads"], kind=res["kind"],
+                                sample=f"best of 3 calls ({gar}, n={n}, f={f}) on d={res['sample_d']} of {d} columns", ms_per_call=best * 1e3,
+                                path=res["path"], cpu_model=res["cpu_model"], cpus_allowed=res["cpus_allowed"], torch=res["torch"])
     # the same operator sequence on CUDA tensors ("PyTorch on B200" incumbent)
     try:
       from oracle import refcost

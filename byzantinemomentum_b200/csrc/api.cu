@@ -19,6 +19,15 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& c = cached[dev & 63];
+  if (c == 0) cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev);
+  return c > 0 ? c : 148;
+}
+
 int check_launch(const char* what) {
   const cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(BZ_ECUDA, "%s: %s", what, cudaGetErrorString(err));

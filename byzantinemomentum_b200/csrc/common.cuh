@@ -40,6 +40,9 @@ struct Geom {
 // Widest usable vector (want_vec, else 1) for these rows / output / optional extra pointer.
 Geom make_geom(const float* const* rows, int n, const void* out, const void* extra, int64_t d, int want_vec);
 
+// SM count of the CURRENT device (cached per device; api.cu)
+int  sm_count();
+
 // Error plumbing (api.cu)
 int  fail(int code, const char* fmt, ...);
 int  check_launch(const char* what);

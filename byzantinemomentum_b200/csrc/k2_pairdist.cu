@@ -406,15 +406,6 @@ k_reduce_parts(const double* __restrict__ parts, int nparts, int len, int pair_n
 
 // ---- host side ---------------------------------------------------------------------------
 
-static int sm_count() {
-  static int cached[64] = {0};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  int& c = cached[dev & 63];
-  if (c == 0) cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev);
-  return c > 0 ? c : 148;
-}
-
 template <int STAGES>
 static void launch_tma(const RowTable& rows, int n, int64_t d, int gx, int gy, int self_pairs, double* parts, cudaStream_t st) {
   const size_t smem = (size_t)STAGES * n * kTmaT * sizeof(float) + 2 * STAGES * sizeof(unsigned long long);

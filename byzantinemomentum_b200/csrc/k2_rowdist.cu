@@ -103,14 +103,6 @@ k2_rowdist(const __grid_constant__ RowTable rows, const int n, const float* __re
   }
 }
 
-static int rd_sm_count() {
-  static int cached[64] = {0};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  int& c = cached[dev & 63];
-  if (c == 0) cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev);
-  return c > 0 ? c : 148;
-}
 
 int launch_rowdist(const RowTable& rows, int n, const float* const* host_rows, const float* center, int64_t d,
                    double* parts, cudaStream_t st, int reverse) {
@@ -118,7 +110,7 @@ int launch_rowdist(const RowTable& rows, int n, const float* const* host_rows, c
   Geom g = make_geom(host_rows, n, center ? (const void*)center : (const void*)host_rows[0], nullptr, d, 4);
   g.reverse = reverse;
   int64_t grid = (g.nv + kRdThreads - 1) / kRdThreads;
-  const int64_t cap = (int64_t)rd_sm_count() * 2;
+  const int64_t cap = (int64_t)sm_count() * 2;
   if (grid > cap) grid = cap;
   if (grid > kMaxParts) grid = kMaxParts;
   if (grid < 1) grid = 1;

@@ -157,16 +157,6 @@ k6_study(const __grid_constant__ RowTable rows, const int n, const Geom g, const
   }
 }
 
-static int st_sm_count() {
-  static int c = 0;
-  if (c == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return c > 0 ? c : 148;
-}
-
 template <int NMAX, int VEC>
 static void launch_one(const RowTable& rows, int n, const Geom& g, float* avg, double* parts, unsigned* bits,
                        double* stats, unsigned grid, cudaStream_t st) {
@@ -186,7 +176,7 @@ void launch_study(const RowTable& rows, int n, const float* const* host_rows, in
   const int want = n <= 16 ? 4 : n <= 32 ? 2 : 1;
   const Geom g = make_geom(host_rows, n, avg, nullptr, d, want);
   int64_t grid = (g.nv + kStThreads - 1) / kStThreads;
-  const int64_t cap = (int64_t)st_sm_count() * 2;
+  const int64_t cap = (int64_t)sm_count() * 2;
   if (grid > cap) grid = cap;
   // the partial blocks are n + 1 doubles wide in a buffer sized kMaxParts * n * n
   const int64_t room = n >= 2 ? kMaxParts : kMaxParts / 2;

@@ -41,13 +41,20 @@ class _Prepared:
 _workspaces = {}
 _staging = {}
 
+_MAX_WORKSPACES = 16
+
 def _workspace(device, stream):
+  """ One scratch buffer per (device, stream), sized for MAX_N (~10 MB).  At most
+  `_MAX_WORKSPACES` are kept (least recently used dropped; the caching allocator keeps a dropped
+  buffer alive until the launches already queued on its stream have run). """
   key = (device.index, stream)
-  ws = _workspaces.get(key)
+  ws = _workspaces.pop(key, None)
   if ws is None:
     nbytes = int(_lib.lib().bz_workspace_bytes(_lib.MAX_N))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-    _workspaces[key] = ws
+    while len(_workspaces) >= _MAX_WORKSPACES:
+      _workspaces.pop(next(iter(_workspaces)))
+  _workspaces[key] = ws          # most recently used last
   return ws
 
 _F32 = torch.float32
@@ -316,7 +323,7 @@ def compute_avg_dev_max(samples):
     return None, math.nan, math.nan, math.nan                 # :105-106
   avg, stats = avg_dev_max_async(samples)
   host = stats.tolist()                                       # the only synchronisation
-  norm_avg = math.sqrt(host[0])
+  norm_avg = ctypes.c_float(math.sqrt(host[0])).value      # :110 returns an fp32 norm: same rounding in the logs
   norm_max = host[1]
   if n >= 2:
     norm_var = 0.

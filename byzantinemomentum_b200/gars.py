@@ -17,6 +17,7 @@ Differences with the reference, all deliberate:
 """
 
 import math
+import weakref
 
 from . import engine
 
@@ -76,20 +77,35 @@ def _bad_m(gradients, f, m):
 # Selection bookkeeping for `influence`
 
 class _Selection:
-  """ Last device-side selection, keyed by the identity and version of the input tensors. """
+  """ Last device-side selection.  The entry is valid only for the very tensor OBJECTS it was
+  computed on (held through weak references, compared with `is`, like `engine._CallCache`),
+  at the same addresses and in-place versions: a freed list whose ids / addresses are reused by
+  new tensors can never match, and a dead reference drops the entry. """
   def __init__(self):
-    self.key = None
-    self.indices = None    # device int32 tensor
+    self.clear()
+  def clear(self):
+    self.rule = self.params = self.refs = self.state = self.indices = None
   @staticmethod
-  def make_key(rule, params, gradients):
-    return (rule, params, tuple((id(g), g.data_ptr(), g._version) for g in gradients))
+  def _state(gradients):
+    return tuple((g.data_ptr(), g._version) for g in gradients)
   def store(self, rule, params, gradients, indices):
-    self.key = self.make_key(rule, params, gradients)
-    self.indices = indices
+    try:
+      refs = tuple(weakref.ref(g) for g in gradients)
+    except TypeError:
+      self.clear()
+      return
+    self.rule, self.params, self.refs, self.state, self.indices = rule, params, refs, self._state(gradients), indices
   def lookup(self, rule, params, gradients):
-    if self.key is not None and self.key == self.make_key(rule, params, gradients):
-      return self.indices
-    return None
+    if self.refs is None or self.rule != rule or self.params != params or len(self.refs) != len(gradients):
+      return None
+    for ref, grad in zip(self.refs, gradients):
+      if ref() is not grad:
+        if ref() is None:
+          self.clear()
+        return None
+    if self._state(gradients) != self.state:
+      return None
+    return self.indices
 
 _last = _Selection()
 

@@ -1,0 +1,129 @@
+# coding: utf-8
+"""The drop-in INSIDE the unmodified reference, on the GPU.
+
+`tools/drive_attack.py` executes the reference's own `attack.py` (from `baseline/_ref`, copied
+verbatim by `tools/install_ref.sh`; nothing of it is edited) with `runpy`, synthetic batches in
+place of the dataset download, and the CUDA rules registered through the reference's own
+`aggregators.register` (`b200-<name>`) and through the `native.<rule>.aggregate` hook it probes
+(`native-<name>`).  Everything of attack.py:799-827 then runs against the CUDA rules on cuda:0:
+the attack's line search (`attacks/identical.py:68-77`: GAR called once per evaluated factor, the
+result modified IN PLACE by `aggregated.sub_(grad_avg)`), `defense.checked(...)`, `influence`
+right after it, the `--device-gar` hops (attack.py:811-815,824-827), the study metrics
+(`tools.compute_avg_dev_max` swapped for the one-pass kernel).
+
+Parity: the same command with the STOCK rule (the reference's own PyTorch code, same device, same
+seed, stock study metrics) must log the same accept ratios and the same study columns up to float
+noise.  All runs share one process (`--batch`): one interpreter start, one CUDA context.
+"""
+
+import json
+import math
+import pathlib
+import subprocess
+import sys
+
+import pytest
+
+import conftest
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+pytestmark = [pytest.mark.gpu, conftest.needs_reference]
+
+STEPS = 3
+EVALS = 4
+
+def _args(out, gar, n, f, attack_args, device="cuda:0", device_gar="same", model="simples-full", dataset="mnist", momentum_at="update"):
+  return ["--gar", gar, "--nb-workers", str(n), "--nb-decl-byz", str(f), "--nb-real-byz", str(f), "--attack", "empire",
+          "--attack-args", *attack_args, "--model", model, "--dataset", dataset, "--nb-steps", str(STEPS), "--device", device,
+          "--device-gar", device_gar, "--batch-size", "8", "--evaluation-delta", "0", "--nb-for-study", str(n - f),
+          "--nb-for-study-past", "2", "--seed", "7", "--momentum-at", momentum_at, "--result-directory", str(out)]
+
+# tag -> (our rule, the stock rule it replaces, n, f, extra keyword arguments of _args)
+LINE_SEARCH = {
+  "b200-krum": ("krum", 11, 3), "native-krum": ("krum", 11, 3), "native-bulyan": ("bulyan", 11, 2), "b200-bulyan": ("bulyan", 15, 3),
+  "b200-trmean": ("trmean", 11, 4), "native-median": ("median", 11, 4), "b200-phocas": ("phocas", 11, 4), "b200-meamed": ("meamed", 11, 4),
+  "native-brute": ("brute", 9, 2), "b200-aksel": ("aksel", 11, 3), "b200-cge": ("cge", 11, 3), "b200-average": ("average", 11, 3),
+}
+OTHER = {
+  # `--device cpu --device-gar cuda:0` (attack.py:811-815,824-827)
+  "hop": ("b200-krum", "krum", 11, 3, dict(attack_args=["factor:1.1"], device="cpu", device_gar="cuda:0")),
+  # `--device cpu`: the rule stages the host rows itself and returns a host tensor
+  "cpu": ("b200-trmean", "trmean", 11, 4, dict(attack_args=["factor:1.1"], device="cpu")),
+  # worker-side momentum (attack.py:799-804: the GAR receives the momentum buffers, updated in
+  # place every step) on CIFAR-10 `empire-cnn` (d = 1,310,922), n = 25, f = 5: BASELINE configs[2]
+  "c3-krum": ("b200-krum", "krum", 25, 5, dict(attack_args=["factor:1.1"], model="empire-cnn", dataset="cifar10", momentum_at="worker")),
+  "c3-bulyan": ("b200-bulyan", "bulyan", 25, 5, dict(attack_args=["factor:1.1"], model="empire-cnn", dataset="cifar10", momentum_at="worker")),
+}
+INFLUENCE = ("krum", "brute", "aksel", "cge", "average")
+
+@pytest.fixture(scope="module")
+def runs(tmp_path_factory):
+  tmp = tmp_path_factory.mktemp("attack")
+  jobs = []
+  for ours, (stock, n, f) in LINE_SEARCH.items():
+    jobs.append(dict(tag=ours, install_tools=True, args=_args(tmp / ours, ours, n, f, [f"factor:-{EVALS}"])))
+    jobs.append(dict(tag=ours + "/stock", install_tools=False, args=_args(tmp / (ours + "-stock"), stock, n, f, [f"factor:-{EVALS}"])))
+  for tag, (ours, stock, n, f, kw) in OTHER.items():
+    jobs.append(dict(tag=tag, install_tools=True, args=_args(tmp / tag, ours, n, f, **kw)))
+    jobs.append(dict(tag=tag + "/stock", install_tools=False, args=_args(tmp / (tag + "-stock"), stock, n, f, **kw)))
+  batch = tmp / "batch.json"
+  batch.write_text(json.dumps(jobs))
+  cmd = [sys.executable, str(ROOT / "tools" / "drive_attack.py"), "--count-calls", "--install-tools", "--batch", str(batch)]
+  proc = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True, timeout=1500)
+  assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
+  result = {}
+  for job in jobs:
+    result[job["tag"]] = dict(ok=False, calls={}, rows=None, dir=pathlib.Path(job["args"][-1]))
+  for line in proc.stdout.splitlines():
+    if line.startswith("run-ok "):
+      result[line.split()[1]]["ok"] = True
+    elif line.startswith("run-failed "):
+      result[line.split()[1]]["error"] = line
+    elif line.startswith("gar-calls "):
+      _, tag, name, calls, infl = line.split()
+      result[tag]["calls"][name] = (int(calls), int(infl))
+  for tag, entry in result.items():
+    study = entry["dir"] / "study"
+    if study.exists():
+      entry["rows"] = [l.split("\t") for l in study.read_text().strip().splitlines()[1:]]
+  result["__stdout__"] = proc.stdout
+  return result
+
+def _close(a, b, rel=2e-4):
+  a, b = float(a), float(b)
+  if math.isnan(a) or math.isnan(b):
+    return math.isnan(a) and math.isnan(b)
+  return abs(a - b) <= rel * max(abs(a), abs(b)) + 2e-6
+
+def _same_study(mine, theirs, exact_ratio, rel=2e-4):
+  assert len(mine) == STEPS and len(theirs) == STEPS
+  for step, (a_row, b_row) in enumerate(zip(mine, theirs)):
+    assert a_row[0] == b_row[0]
+    if exact_ratio:      # a count of selected attack rows over a count: exact
+      assert float(a_row[-1]) == float(b_row[-1]), (step, a_row[-1], b_row[-1])
+    else:
+      assert math.isnan(float(a_row[-1])) and math.isnan(float(b_row[-1]))
+    for col, (a, b) in enumerate(zip(a_row[2:-1], b_row[2:-1])):
+      assert _close(a, b, rel), (step, col + 2, a, b)
+
+@pytest.mark.parametrize("ours", sorted(LINE_SEARCH))
+def test_attack_py_with_line_search_matches_the_stock_rule(runs, ours):
+  """ empire with factor:-4 = a 4-evaluation line search per step -> 5 GAR calls per step, the
+  fifth followed by influence() (attack.py:821-822). """
+  stock = LINE_SEARCH[ours][0]
+  mine, theirs = runs[ours], runs[ours + "/stock"]
+  assert mine["ok"], mine.get("error", runs["__stdout__"][-3000:])
+  assert theirs["ok"], theirs.get("error")
+  has_influence = stock in INFLUENCE
+  assert mine["calls"][ours] == (STEPS * (EVALS + 1), STEPS if has_influence else 0), mine["calls"]
+  assert theirs["calls"][stock][0] == STEPS * (EVALS + 1)
+  _same_study(mine["rows"], theirs["rows"], has_influence)
+
+@pytest.mark.parametrize("tag", sorted(OTHER))
+def test_attack_py_device_hops_momentum_and_cifar_shape(runs, tag):
+  ours, stock = OTHER[tag][0], OTHER[tag][1]
+  mine, theirs = runs[tag], runs[tag + "/stock"]
+  assert mine["ok"], mine.get("error", runs["__stdout__"][-3000:])
+  assert theirs["ok"], theirs.get("error")
+  assert mine["calls"][ours][0] == STEPS
+  _same_study(mine["rows"], theirs["rows"], stock in INFLUENCE, rel=5e-4)

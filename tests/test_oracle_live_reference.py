@@ -15,7 +15,7 @@ import conftest
 from test_oracle_golden import test_oracle_matches_reference as check_call
 
 ROOT = pathlib.Path(__file__).resolve().parent.parent
-REF = pathlib.Path(os.environ.get("BYZ_REFERENCE", "/root/reference"))
+REF = conftest.reference_root() or pathlib.Path("/nonexistent")
 
 # (name, kind, n, nb_byz, d, seed, fs) — none of them is a committed fixture
 LIVE_CASES = [
@@ -45,7 +45,8 @@ for case in {cases!r}:
 def test_oracle_matches_fresh_reference_outputs(tmp_path):
   script = tmp_path / "gen.py"
   script.write_text(SCRIPT.format(golden_dir=str(ROOT / "tests" / "golden"), cases=LIVE_CASES, out_dir=str(tmp_path)))
-  proc = subprocess.run([sys.executable, str(script)], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+  proc = subprocess.run([sys.executable, str(script)], cwd=tmp_path, capture_output=True, text=True, timeout=900,
+                        env=dict(os.environ, BYZ_REFERENCE=str(REF)))
   assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-3000:]
   checked = 0
   for path in sorted(tmp_path.glob("golden_live_*.npz")):

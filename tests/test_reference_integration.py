@@ -10,8 +10,10 @@ import sys
 
 import pytest
 
+import conftest
+
 ROOT = pathlib.Path(__file__).resolve().parent.parent
-REF = pathlib.Path(os.environ.get("BYZ_REFERENCE", "/root/reference"))
+REF = conftest.reference_root() or pathlib.Path("/nonexistent")
 
 SCRIPT = r"""
 import sys

@@ -25,16 +25,24 @@ SHAPES = {"mnist": ((1, 28, 28), 10), "cifar10": ((3, 32, 32), 10), "cifar100": 
 
 def main():
   parser = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
-  parser.add_argument("--reference", required=True, help="root of the ByzantineMomentum checkout")
+  parser.add_argument("--reference", default=None, help="root of the ByzantineMomentum checkout (default: $BYZ_REFERENCE, baseline/_ref, /root/reference)")
+  parser.add_argument("--count-calls", action="store_true", help="count the calls of every registered rule and its influence(); print `gar-calls <tag> <name> <calls> <influence calls>` lines after each run")
   parser.add_argument("--shape", default="mnist", choices=sorted(SHAPES), help="shape of the synthetic samples")
   parser.add_argument("--override", action="store_true", help="replace the stock rules instead of adding b200-<name>")
   parser.add_argument("--install-tools", action="store_true", help="also swap tools.compute_avg_dev_max for CUDA samples")
+  parser.add_argument("--batch", default=None, help="JSON file with a list of {tag, args}: run attack.py once per entry in this process")
   parser.add_argument("rest", nargs=argparse.REMAINDER, help="arguments of attack.py (after --)")
   args = parser.parse_args()
   rest = args.rest[1:] if args.rest[:1] == ["--"] else args.rest
-  ref = pathlib.Path(args.reference).resolve()
   root = pathlib.Path(__file__).resolve().parent.parent
   sys.path.insert(0, str(root))
+  if args.reference is None:
+    from oracle import reference as refloc      # locating only: the run below is the reference's own code
+    ref = refloc.find_root()
+    if ref is None:
+      raise SystemExit("no reference found (run tools/install_ref.sh or pass --reference)")
+  else:
+    ref = pathlib.Path(args.reference).resolve()
   sys.path.insert(0, str(ref))
 
   import torch
@@ -43,8 +51,9 @@ def main():
   import tools
   import byzantinemomentum_b200 as bz
 
-  sample_shape, classes = SHAPES[args.shape]
   def make_datasets(dataset, train_batch, test_batch, **kwargs):
+    # the shape follows attack.py's --dataset when it names a known one, else --shape
+    sample_shape, classes = SHAPES.get(str(dataset).lower(), SHAPES[args.shape])
     def batches(size, seed):
       gen = torch.Generator().manual_seed(seed)
       while True:
@@ -54,11 +63,51 @@ def main():
   experiments.make_datasets = make_datasets
 
   names = bz.plugin.install(aggregators, override=args.override)
+  stock_study = tools.compute_avg_dev_max
   if args.install_tools:
     bz.plugin.install_tools(tools)
+  cuda_study = tools.compute_avg_dev_max
   print(f"registered: {', '.join(names)}", flush=True)
+  counts = {}
+  if args.count_calls:
+    def counted(fn, slot, key):
+      def wrapper(*a, **kw):
+        counts[key][slot] += 1
+        return fn(*a, **kw)
+      return wrapper
+    for key, rule in list(aggregators.gars.items()):
+      counts[key] = [0, 0]
+      # attack.py:468 fetched nothing yet: rebuild the entry around counting closures with the
+      # reference's own make_gar (aggregators/__init__.py:42-69)
+      wrapped = aggregators.make_gar(counted(rule.unchecked, 0, key), rule.check, upper_bound=rule.upper_bound,
+                                     influence=None if rule.influence is None else counted(rule.influence, 1, key))
+      aggregators.gars[key] = wrapped
+  stream = sys.__stdout__
+  def report(tag):
+    for key, pair in counts.items():
+      if pair[0] or pair[1]:
+        stream.write(f"gar-calls {tag} {key} {pair[0]} {pair[1]}\n")
+      pair[0] = pair[1] = 0
+    stream.flush()
+  if args.batch:
+    # several attack.py runs in ONE process (one interpreter start, one CUDA context)
+    import json, traceback
+    for job in json.loads(pathlib.Path(args.batch).read_text()):
+      sys.argv = [str(ref / "attack.py")] + list(job["args"])
+      tools.compute_avg_dev_max = cuda_study if job.get("install_tools", True) else stock_study
+      try:
+        runpy.run_path(str(ref / "attack.py"), run_name="__main__")
+        stream.write(f"run-ok {job['tag']}\n")
+      except BaseException as err:      # attack.py reports fatal errors through exit(1)
+        stream.write(f"run-failed {job['tag']} {type(err).__name__}: {err}\n")
+        traceback.print_exc(file=stream)
+      report(job["tag"])
+    return
   sys.argv = [str(ref / "attack.py")] + rest
-  runpy.run_path(str(ref / "attack.py"), run_name="__main__")
+  try:
+    runpy.run_path(str(ref / "attack.py"), run_name="__main__")
+  finally:
+    report("run")
 
 if __name__ == "__main__":
   main()
