@@ -31,6 +31,15 @@ bool carve_workspace(void* ws, size_t bytes, int n, Workspace& out);
 // the alias map of K5.
 int launch_pairdist(const RowTable& rows, int n, int64_t d, double* parts, cudaStream_t st, int self_pairs = 0);
 
+// K2, second generation (k2_ring.cu): balanced tasks, distributed TMA issue, clusters + multicast for
+// n > 25.  Returns the number of blocks written or -1 when it cannot run (unaligned rows, ...).
+int launch_pairdist_ring(const RowTable& rows, int n, int64_t d, double* parts, cudaStream_t st,
+                         const unsigned char* self_rows, int nself);
+// Dispatcher used by the rules: `rows` are the u unique rows, `to_unique` (or NULL) maps the n_orig
+// original rows to them; the self distance is produced for the unique rows that are aliased.
+int launch_pairdist_auto(const RowTable& rows, int u, int64_t d, double* parts, cudaStream_t st,
+                         const int* to_unique, int n_orig);
+
 // K2': parts[x*n + i] = share of sum_k (rows[i][k] - center[k])^2 (center NULL: the origin).
 int launch_rowdist(const RowTable& rows, int n, const float* const* host_rows, const float* center, int64_t d,
                    double* parts, cudaStream_t st, int reverse = 0);

@@ -20,10 +20,9 @@
 
 #include "dist.cuh"
 #include "reduce.cuh"
+#include "tma.cuh"
 
 namespace bz {
-
-typedef unsigned long long u64;
 
 constexpr int kG = 5;
 constexpr int kK2Warps = 16;
@@ -38,20 +37,6 @@ __device__ __forceinline__ void cp_async16(float* smem, const float* gmem, int s
 __device__ __forceinline__ void cp_async4(float* smem, const float* gmem, int src_bytes) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
-}
-
-__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
-  u64 d;
-  asm("sub.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
-  u64 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ float half_sum(u64 v) {
-  return __fadd_rn(__uint_as_float((unsigned)(v & 0xffffffffull)), __uint_as_float((unsigned)(v >> 32)));
 }
 
 // Stage tile [base, base+T) of every row into buf[n][T]; zero fill past d.
@@ -234,45 +219,6 @@ constexpr int kTmaLogQ = (kTmaT == 256) ? 6 : (kTmaT == 512) ? 7 : 8;   // log2(
 #endif
 constexpr int kTmaFlush = (1024 / kTmaT) * BZ_K2_FLUSH_SCALE;   // tiles between flushes: <= 16 terms per accumulator half
 static_assert(kTmaT == 256 || kTmaT == 512 || kTmaT == 1024, "BZ_K2_TMA_T");
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// BZ_MBAR_HINT_NS (A/B builds): suspend-time hint of try_wait.  Without it the hardware wait is
-// short and a waiting warp re-issues the probe ~28 times per tile (ncu, n = 25: SYNCS + BRA + YIELD
-// = 11 % of the executed instructions, on the schedulers the working warps need).
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-#ifdef BZ_MBAR_HINT_NS
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}"
-      ::"r"(smem_u32(bar)), "r"(parity), "r"((unsigned)BZ_MBAR_HINT_NS) : "memory");
-#else
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}"
-      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-#endif
-}
-__device__ __forceinline__ void tma_load_1d(float* dst, const float* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 
 template <int STAGES>
 __global__ void __launch_bounds__(kK2Threads, 1)
@@ -467,6 +413,25 @@ int launch_pairdist(const RowTable& rows, int n, int64_t d, double* parts, cudaS
   if ((int64_t)gx > ntiles) gx = (int)(ntiles > 0 ? ntiles : 1);
   k2_pairdist<<<dim3(gx, gy > 0 ? gy : 1), kK2Threads, smem, st>>>(rows, n, T, logq, d, ntiles, self_pairs, parts);
   return gx;
+}
+
+int launch_pairdist_auto(const RowTable& rows, int u, int64_t d, double* parts, cudaStream_t st,
+                         const int* to_unique, int n_orig) {
+  unsigned char self_rows[kMaxN];
+  int nself = 0;
+  if (to_unique != nullptr && u < n_orig) {
+    int mult[kMaxN] = {0};
+    for (int i = 0; i < n_orig; ++i) ++mult[to_unique[i]];
+    for (int k = 0; k < u; ++k)
+      if (mult[k] > 1) self_rows[nself++] = (unsigned char)k;
+  }
+  const char* env = getenv("BYZAGG_K2_LEGACY");     // read per call: tools/k2_ab.py flips it between launches
+  const bool legacy = env != nullptr && env[0] == '1';
+  if (!legacy) {
+    const int nparts = launch_pairdist_ring(rows, u, d, parts, st, self_rows, nself);
+    if (nparts > 0) return nparts;
+  }
+  return launch_pairdist(rows, u, d, parts, st, nself > 0 ? 1 : 0);
 }
 
 void launch_reduce_parts(const double* parts, int nparts, int len, int pair_n, double* block, cudaStream_t st) {

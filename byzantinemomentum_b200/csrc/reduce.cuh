@@ -5,6 +5,24 @@
 
 namespace bz {
 
+typedef unsigned long long u64;
+
+// Packed fp32 pairs (two coordinates per instruction: SASS FADD2 / FFMA2)
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+  u64 d;
+  asm("sub.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float half_sum(u64 v) {
+  return __fadd_rn(__uint_as_float((unsigned)(v & 0xffffffffull)), __uint_as_float((unsigned)(v >> 32)));
+}
+
+
 // Transposed warp reduction: on return, lane L holds sum over lanes of v[L] (v has 32 slots).
 __device__ __forceinline__ float transpose_reduce(float (&v)[32], int lane) {
 #pragma unroll

@@ -95,12 +95,14 @@ def _close(a, b, rel=2e-4):
     return math.isnan(a) and math.isnan(b)
   return abs(a - b) <= rel * max(abs(a), abs(b)) + 2e-6
 
-def _same_study(mine, theirs, exact_ratio, rel=2e-4):
+def _same_study(mine, theirs, exact_ratio, rel=2e-4, ratio_nan=False):
   assert len(mine) == STEPS and len(theirs) == STEPS
   for step, (a_row, b_row) in enumerate(zip(mine, theirs)):
     assert a_row[0] == b_row[0]
     if exact_ratio:      # a count of selected attack rows over a count: exact
       assert float(a_row[-1]) == float(b_row[-1]), (step, a_row[-1], b_row[-1])
+    elif ratio_nan:
+      assert math.isnan(float(a_row[-1]))
     else:
       assert math.isnan(float(a_row[-1])) and math.isnan(float(b_row[-1]))
     for col, (a, b) in enumerate(zip(a_row[2:-1], b_row[2:-1])):
@@ -114,10 +116,11 @@ def test_attack_py_with_line_search_matches_the_stock_rule(runs, ours):
   mine, theirs = runs[ours], runs[ours + "/stock"]
   assert mine["ok"], mine.get("error", runs["__stdout__"][-3000:])
   assert theirs["ok"], theirs.get("error")
-  has_influence = stock in INFLUENCE
+  # the reference registers its native-<name> rules WITHOUT influence (krum.py:159-166): nan there
+  has_influence = stock in INFLUENCE and not ours.startswith("native-")
   assert mine["calls"][ours] == (STEPS * (EVALS + 1), STEPS if has_influence else 0), mine["calls"]
   assert theirs["calls"][stock][0] == STEPS * (EVALS + 1)
-  _same_study(mine["rows"], theirs["rows"], has_influence)
+  _same_study(mine["rows"], theirs["rows"], has_influence, ratio_nan=not has_influence)
 
 @pytest.mark.parametrize("tag", sorted(OTHER))
 def test_attack_py_device_hops_momentum_and_cifar_shape(runs, tag):

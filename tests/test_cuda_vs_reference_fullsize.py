@@ -100,8 +100,23 @@ def test_c3_krum_bulyan_and_the_other_distance_rules(ref):
     want = _np(ref.gars["bulyan"].unchecked(gradients=cpu, f=f))
     got = _np(bz.gars["bulyan"](gradients=dev, f=f))
     # stage 2 is a closest-beta mean in topk's unspecified order: 1e-6 of the summed magnitude
-    # (a different stage-1 selection would move whole coordinates by O(1))
-    parity.assert_close_scaled(got, want, parity.column_scale(x), f"C3 bulyan {dist}", rtol=2e-6)
+    # (a different stage-1 selection would move whole coordinates by O(1)).  Coordinates with an
+    # exact key tie across the closest-beta boundary (a handful in 1.3M) have two valid answers:
+    # they are identified by redoing stages 1-2 with the oracle on exactly those columns.
+    scale = parity.column_scale(x)
+    off = np.abs(got.astype(np.float64) - want) > 2e-6 * np.maximum(np.abs(want), scale)
+    exempt = np.zeros(d, dtype=bool)
+    if off.any():
+      cols = np.flatnonzero(off)
+      assert cols.size <= 50, f"C3 bulyan {dist}: {cols.size} coordinates differ"
+      from oracle import byzoracle as orc, corc
+      host = [_np(r) for r in cpu]
+      D = corc.pairwise_distances(host)
+      border, _ = orc.bulyan_order(D, f, n - f - 2)
+      stage1 = orc.bulyan_stage1(orc.as_matrix([h[cols] for h in host]), border, f, n - f - 2)
+      _, amb = orc.closest_mean(stage1, stage1.shape[0] - 2 * f, orc.median(stage1), return_info=True)
+      exempt[cols] = amb
+    parity.assert_close_scaled(got, want, scale, f"C3 bulyan {dist}", rtol=2e-6, exempt=exempt)
 
 def test_c5_brute(ref):
   import byzantinemomentum_b200 as bz
