@@ -19,6 +19,7 @@ size_t workspace_bytes(int n);
 struct Workspace {
   int32_t* order;     // n entries
   int32_t* status;    // 1 entry
+  unsigned* ticket;   // 1 entry (last-CTA election of the fused scoring step)
   double*  block;     // n*n
   double*  parts;     // kMaxParts * n*n
 };
@@ -33,12 +34,25 @@ int launch_pairdist(const RowTable& rows, int n, int64_t d, double* parts, cudaS
 
 // K2, second generation (k2_ring.cu): balanced tasks, distributed TMA issue, clusters + multicast for
 // n > 25.  Returns the number of blocks written or -1 when it cannot run (unaligned rows, ...).
+// Optional scoring / selection step to run inside the distance pass (its last CTA): what the
+// caller would otherwise launch as K5.  `fused` is set when the pass did run it.
+struct SelectTail {
+  int kind;                 // 1 = Multi-Krum order, 2 = Bulyan order + status, 3 = brute subset,
+                            // 4 = the reduced block only (phase A of the sharded path): `order` is a double[n*n]
+  int n, f, m, count;       // n = ORIGINAL row count
+  unsigned long long total; // brute: C(n, n - f)
+  const int* to_unique;     // original row -> unique row (NULL: identity)
+  int32_t* order;
+  int32_t* status;
+  unsigned* ticket;         // 128 bytes of device scratch
+  int fused;
+};
 int launch_pairdist_ring(const RowTable& rows, int n, int64_t d, double* parts, cudaStream_t st,
-                         const unsigned char* self_rows, int nself);
+                         const unsigned char* self_rows, int nself, SelectTail* select = nullptr);
 // Dispatcher used by the rules: `rows` are the u unique rows, `to_unique` (or NULL) maps the n_orig
 // original rows to them; the self distance is produced for the unique rows that are aliased.
 int launch_pairdist_auto(const RowTable& rows, int u, int64_t d, double* parts, cudaStream_t st,
-                         const int* to_unique, int n_orig);
+                         const int* to_unique, int n_orig, SelectTail* select = nullptr);
 
 // K2': parts[x*n + i] = share of sum_k (rows[i][k] - center[k])^2 (center NULL: the origin).
 int launch_rowdist(const RowTable& rows, int n, const float* const* host_rows, const float* center, int64_t d,
@@ -55,6 +69,18 @@ void launch_study(const RowTable& rows, int n, const float* const* host_rows, in
 // pair_n > 0: the block is a pair_n x pair_n table of which only entries i < j are defined; the
 // others are written as 0.
 void launch_reduce_parts(const double* parts, int nparts, int len, int pair_n, double* block, cudaStream_t st);
+
+// C(n, n - f), saturating at 2^64 - 1.
+inline unsigned long long brute_total(int n, int f) {
+  const int k = n - f;
+  unsigned long long total = 1;
+  for (int i = 1; i <= (k < n - k ? k : n - k); ++i) {
+    const unsigned long long num = (unsigned long long)(n - i + 1);
+    if (total > (~0ull) / num) return ~0ull;
+    total = total * num / i;
+  }
+  return total;
+}
 
 // ---- K5: scoring / selection (single CTA each) --------------------------------------------------
 // to_unique[n] / u: optional alias map (rows i, j with to_unique[i] == to_unique[j] are the same

@@ -416,7 +416,7 @@ int launch_pairdist(const RowTable& rows, int n, int64_t d, double* parts, cudaS
 }
 
 int launch_pairdist_auto(const RowTable& rows, int u, int64_t d, double* parts, cudaStream_t st,
-                         const int* to_unique, int n_orig) {
+                         const int* to_unique, int n_orig, SelectTail* select) {
   unsigned char self_rows[kMaxN];
   int nself = 0;
   if (to_unique != nullptr && u < n_orig) {
@@ -428,9 +428,10 @@ int launch_pairdist_auto(const RowTable& rows, int u, int64_t d, double* parts, 
   const char* env = getenv("BYZAGG_K2_LEGACY");     // read per call: tools/k2_ab.py flips it between launches
   const bool legacy = env != nullptr && env[0] == '1';
   if (!legacy) {
-    const int nparts = launch_pairdist_ring(rows, u, d, parts, st, self_rows, nself);
+    const int nparts = launch_pairdist_ring(rows, u, d, parts, st, self_rows, nself, select);
     if (nparts > 0) return nparts;
   }
+  if (select != nullptr) select->fused = 0;
   return launch_pairdist(rows, u, d, parts, st, nself > 0 ? 1 : 0);
 }
 

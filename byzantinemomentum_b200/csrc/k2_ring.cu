@@ -30,6 +30,7 @@
 #include <cstdlib>
 
 #include "dist.cuh"
+#include "k5_device.cuh"
 #include "reduce.cuh"
 #include "tma.cuh"
 
@@ -42,6 +43,8 @@ constexpr int kRSlots = kG * kG;
 constexpr size_t kRSmemBudget = 226 * 1024;
 constexpr int kRMaxCluster = 8;
 constexpr int kSelfPerWarp = 3;
+constexpr int kTailGroup = 16;           // clusters per first-level group of the fused reduction
+constexpr int kTailTickets = 32;         // words of ticket scratch (1 + number of groups)
 // fp32 terms per accumulator half between two flushes into fp64.  32: worst-case relative error
 // 32 * 2^-24 = 1.9e-6 on one lane partial if every rounding went the same way; measured against
 // fp64 (tools/k2_ab.py) the summed distance is within 1e-8.
@@ -53,6 +56,19 @@ constexpr int kSelfPerWarp = 3;
 struct SelfList {
   unsigned char row[kRWarps * kRMaxCluster * kSelfPerWarp];
   int count;
+};
+
+// Scoring / selection run by the LAST CTA to finish (ticket), in the shared memory the ring no
+// longer needs: the rule's K5 step without its launch (k5_device.cuh).
+struct RingTail {
+  int kind;                 // 0 = none, 1 = Multi-Krum order, 2 = Bulyan order + status, 3 = brute subset,
+                            // 4 = only the reduced u x u block, written to `order` (a double*)
+  int n, f, m, count, slices;
+  unsigned long long total; // brute: C(n, n - f)
+  int32_t* order;
+  int32_t* status;
+  unsigned* ticket;         // kTailTickets words, zero before the launch; left at zero
+  RowMap map;               // original rows -> unique rows
 };
 
 // ---- cluster helpers -------------------------------------------------------------------------
@@ -241,8 +257,8 @@ __device__ __forceinline__ void ring_stage_tail(float* buf, const RowTable& rows
 // parts[cluster * n * n + i * n + j] (i < j; i == j for the rows of `self`).
 template <int T, int STAGES, bool SELF, bool CLUSTER>
 __global__ void __launch_bounds__(kRThreads, 1)
-k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList self, const int n, const int csize,
-        const int64_t d, const int64_t nfull, double* __restrict__ parts) {
+k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList self, const __grid_constant__ RingTail tail,
+        const int n, const int csize, const int64_t d, const int64_t nfull, double* __restrict__ parts) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ng = (n + kG - 1) / kG;
@@ -354,11 +370,21 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
         for (int r = 0; r < C; ++r) mbar_arrive_remote(&empty[s], (unsigned)r);
     }
     if (task.kind != 0 && ++pending == kFlushTiles) { pending = 0; ring_flush(acc, lane, dacc); }
-    // refill the stage released one iteration ago (every warp of the cluster is past it by now)
-    if (refiller && k >= 1 && issued < mine) {
-      mbar_wait(&empty[sp], pp);
-      refill(sp);
-      ++issued;
+    if (STAGES >= 3) {
+      // refill the stage released one iteration ago (every warp of the cluster is past it by now)
+      if (refiller && k >= 1 && issued < mine) {
+        mbar_wait(&empty[sp], pp);
+        refill(sp);
+        ++issued;
+      }
+    } else {
+      // two stages (large tiles of many rows): no slack to defer, refill this stage as soon as the
+      // whole cluster has released it
+      if (refiller && issued < mine) {
+        mbar_wait(&empty[s], parity);
+        refill(s);
+        ++issued;
+      }
     }
     sp = s; pp = parity;
     if (++s == STAGES) { s = 0; parity ^= 1u; }
@@ -414,13 +440,66 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
       }
     }
   }
+  if (tail.kind != 0) {
+    // Two-level, fixed-order reduction of the per-cluster blocks followed by the scoring step, all
+    // inside this launch.  One CTA pulling 148 blocks alone is bandwidth-starved (a single SM:
+    // ~10 us for 740 KB at n = 25), so the blocks are first summed by groups of kTailGroup clusters
+    // — by whichever CTA of the group finishes last, but always in index order: deterministic —
+    // and the last group to finish sums the <= 10 group blocks and runs the selection in the
+    // shared memory the ring no longer needs (every other CTA is past its ring by then).
+    __shared__ int elected;
+    const int len = n * n;
+    const int ngroups = (nclusters + kTailGroup - 1) / kTailGroup;
+    const int group = cluster_id / kTailGroup;
+    const int first = group * kTailGroup;
+    const int members = min(kTailGroup, nclusters - first);
+    double* gblocks = parts + (size_t)nclusters * len;            // behind the per-cluster blocks
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) elected = (atomicAdd(tail.ticket + 1 + group, 1u) == (unsigned)(members * C) - 1u) ? 1 : 0;
+    __syncthreads();
+    if (elected) {
+      __threadfence();
+      for (int e = threadIdx.x; e < len; e += kRThreads) {
+        double v[kTailGroup];
+#pragma unroll
+        for (int p = 0; p < kTailGroup; ++p) v[p] = (p < members) ? __ldcg(parts + (size_t)(first + p) * len + e) : 0.;
+        double sum = v[0];
+#pragma unroll
+        for (int p = 1; p < kTailGroup; ++p) sum += v[p];          // + 0.0 past `members`: exact
+        gblocks[(size_t)group * len + e] = sum;
+      }
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) elected = (atomicAdd(tail.ticket, 1u) == (unsigned)ngroups - 1u) ? 1 : 0;
+      __syncthreads();
+      if (elected) {
+        __threadfence();
+        double* sm = reinterpret_cast<double*>(smem_raw);
+        const StridedParts all{gblocks, (size_t)len};
+        if (tail.kind == 4) {
+          // phase A of the d-sharded path: this rank's reduced block (entries outside i < j are 0)
+          double* out_block = reinterpret_cast<double*>(tail.order);
+          for (int e = threadIdx.x; e < len; e += kRThreads) {
+            double sum = 0.;
+            for (int g = 0; g < ngroups; ++g) sum += __ldcg(gblocks + (size_t)g * len + e);
+            out_block[e] = (e / n < e % n) ? sum : 0.;
+          }
+        }
+        else if (tail.kind == 3) brute_select_body(all, tail.map, ngroups, tail.n, tail.f, tail.total, tail.order, tail.status, tail.slices, sm);
+        else                score_select_body(all, tail.map, ngroups, tail.n, tail.count, tail.order, tail.kind == 2 ? tail.status : nullptr,
+                                              tail.f, tail.m, tail.kind == 2 ? 1 : 0, tail.slices, sm);
+        if (threadIdx.x <= ngroups) tail.ticket[threadIdx.x] = 0u;
+      }
+    }
+  }
   if (CLUSTER) cluster_sync_all();   // no CTA leaves while a peer may still arrive on its barriers
 }
 
 // ---- host side -------------------------------------------------------------------------------
 
 template <int T, int STAGES, bool SELF, bool CLUSTER>
-static int launch_ring_cfg(const RowTable& rows, const SelfList& self, int n, int C, int64_t d, double* parts, cudaStream_t st) {
+static int launch_ring_cfg(const RowTable& rows, const SelfList& self, RingTail& tail, int n, int C, int64_t d, double* parts, cudaStream_t st) {
   const int ng = (n + kG - 1) / kG;
   const size_t smem = (size_t)STAGES * ng * kG * T * sizeof(float) + 2 * STAGES * sizeof(unsigned long long);
   auto kernel = k2_ring<T, STAGES, SELF, CLUSTER>;
@@ -457,11 +536,24 @@ static int launch_ring_cfg(const RowTable& rows, const SelfList& self, int n, in
     if (cached < 1) return -1;                 // this cluster size cannot be scheduled here
     if (nclusters > cached) nclusters = cached;  // persistent kernel: only co-resident clusters
   }
-  if (nclusters > kMaxParts) nclusters = kMaxParts;
+  if (nclusters > kMaxParts - kTailTickets) nclusters = kMaxParts - kTailTickets;   // room for the group blocks behind
   if ((int64_t)nclusters > ntiles) nclusters = (int)(ntiles > 0 ? ntiles : 1);
   if (nclusters < 1) nclusters = 1;
   cfg.gridDim = dim3((unsigned)(nclusters * C));
-  if (cudaLaunchKernelEx(&cfg, kernel, rows, self, n, C, d, nfull, parts) != cudaSuccess) return -1;
+  if (tail.kind != 0) {
+    // the tail works in the ring's stage area (the barriers behind it stay untouched)
+    const size_t avail = (size_t)STAGES * ng * kG * T * sizeof(float);
+    const size_t nn = (size_t)tail.n * tail.n * sizeof(double);
+    const size_t fixed = tail.kind == 3 ? nn + (size_t)(tail.n + 1) * (tail.n + 1) * sizeof(unsigned long long) + 64 * sizeof(double)
+                                        : 2 * nn + (size_t)tail.n * sizeof(double);
+    if (tail.kind != 4 && avail < fixed + nn) tail.kind = 0;     // does not fit: the caller launches K5 itself
+    else {
+      const int ngroups = (nclusters + kTailGroup - 1) / kTailGroup;
+      tail.slices = tail.kind == 4 ? 1 : pick_slices(tail.n, ngroups, kRThreads, avail - fixed);
+      cudaMemsetAsync(tail.ticket, 0, kTailTickets * sizeof(unsigned), st);
+    }
+  }
+  if (cudaLaunchKernelEx(&cfg, kernel, rows, self, tail, n, C, d, nfull, parts) != cudaSuccess) return -1;
   return nclusters;
 }
 
@@ -475,7 +567,7 @@ int ring_cluster_size(int n) {
 // Returns the number of partial blocks written, or -1 when the configuration cannot run here
 // (the caller falls back to k2_pairdist).  `self_rows`: unique rows whose self distance K5 reads.
 int launch_pairdist_ring(const RowTable& rows, int n, int64_t d, double* parts, cudaStream_t st,
-                         const unsigned char* self_rows, int nself) {
+                         const unsigned char* self_rows, int nself, SelectTail* select) {
   const char* env = getenv("BYZAGG_K2_CLUSTER");
   const int force_cluster = env ? atoi(env) : 0;
   int C = ring_cluster_size(n);
@@ -490,14 +582,27 @@ int launch_pairdist_ring(const RowTable& rows, int n, int64_t d, double* parts, 
   const int ng = (n + kG - 1) / kG;
   const int rows_alloc = ng * kG;
   const bool selfk = nself > 0;
-#define BZ_RING(T, S, CL) (selfk ? launch_ring_cfg<T, S, true, CL>(rows, self, n, C, d, parts, st) : launch_ring_cfg<T, S, false, CL>(rows, self, n, C, d, parts, st))
-  if (C == 1) {
-    if (rows_alloc <= 25) return BZ_RING(512, 4, false);
-    return -1;
+  RingTail tail = {};
+  const char* nofuse = getenv("BYZAGG_K2_NOFUSE");
+  if (select != nullptr && select->kind != 0 && !(nofuse && nofuse[0] == '1')) {
+    tail.kind = select->kind; tail.n = select->n; tail.f = select->f; tail.m = select->m; tail.count = select->count;
+    tail.total = select->total; tail.order = select->order; tail.status = select->status; tail.ticket = select->ticket;
+    tail.map = make_map(select->to_unique, select->n, n);
   }
-  if (rows_alloc <= 35) return BZ_RING(512, 3, true);
-  return BZ_RING(256, 3, true);
+#define BZ_RING(T, S, CL) (selfk ? launch_ring_cfg<T, S, true, CL>(rows, self, tail, n, C, d, parts, st) : launch_ring_cfg<T, S, false, CL>(rows, self, tail, n, C, d, parts, st))
+  int nparts;
+  if (C == 1) {
+    if (rows_alloc > 25) return -1;
+    nparts = BZ_RING(512, 4, false);
+  } else if (rows_alloc <= 35) nparts = BZ_RING(512, 3, true);
+  else {
+    const char* big = getenv("BYZAGG_K2_BIGTILE");
+    if (rows_alloc <= 55 && big && big[0] == '1') nparts = BZ_RING(512, 2, true);
+    else                                          nparts = BZ_RING(256, 3, true);
+  }
 #undef BZ_RING
+  if (select != nullptr) select->fused = (nparts > 0 && tail.kind != 0) ? 1 : 0;
+  return nparts;
 }
 
 }  // namespace bz

@@ -62,6 +62,7 @@ k3_average(const __grid_constant__ RowTable rows, const Geom g, const int32_t* _
   if (v >= g.nv) return;
   const int64_t e0 = v * VEC - g.shift;
   const bool full = e0 >= 0 && e0 + VEC <= g.d;
+  pdl_wait();        // launched while the scoring step drains: the selection / status / rows are valid from here
   if (status != nullptr && *status != 0) {
     float nan[VEC];
 #pragma unroll
@@ -77,9 +78,9 @@ void launch_average(const RowTable& rows, const Geom& g, const int32_t* sel, int
                     int zero_init, float divisor, const int32_t* status, float* out, cudaStream_t st) {
   if (g.nv <= 0) return;
   const unsigned blocks = (unsigned)((g.nv + kK3Threads - 1) / kK3Threads);
-  if (g.vec == 4)      k3_average<4><<<blocks, kK3Threads, 0, st>>>(rows, g, sel, count, zero_init, divisor, status, out);
-  else if (g.vec == 2) k3_average<2><<<blocks, kK3Threads, 0, st>>>(rows, g, sel, count, zero_init, divisor, status, out);
-  else                 k3_average<1><<<blocks, kK3Threads, 0, st>>>(rows, g, sel, count, zero_init, divisor, status, out);
+  if (g.vec == 4)      launch_after(k3_average<4>, blocks, kK3Threads, 0, st, rows, g, sel, count, zero_init, divisor, status, out);
+  else if (g.vec == 2) launch_after(k3_average<2>, blocks, kK3Threads, 0, st, rows, g, sel, count, zero_init, divisor, status, out);
+  else                 launch_after(k3_average<1>, blocks, kK3Threads, 0, st, rows, g, sel, count, zero_init, divisor, status, out);
 }
 
 }  // namespace bz

@@ -10,6 +10,7 @@
 // averages sorted positions i .. i+m_i-1 with m_i = min(m, m_max - i).
 // Roofline: HBM, (m_max + 1)·4 B per coordinate.
 #include "dist.cuh"
+#include "launch.cuh"
 #include "networks_gen.cuh"
 
 namespace bz {
@@ -25,6 +26,7 @@ k4_bulyan(const __grid_constant__ RowTable rows, const int64_t d, const int n, c
   const int64_t i = ((int64_t)gridDim.x - 1 - blockIdx.x) * kK4Threads + threadIdx.x;
   if (i >= d) return;
   const int64_t e = i;
+  pdl_wait();        // PDL: order / status / rows are valid from here
   if (status != nullptr && *status != 0) { out[e] = quiet_nan(); return; }
   float* col = sm + threadIdx.x;
   const int m_max = n - f - 2;
@@ -89,6 +91,7 @@ k4_bulyan_static(const __grid_constant__ RowTable rows, const Geom g, const int3
   const int64_t e0 = v * VEC - g.shift;
   const bool full = e0 >= 0 && e0 + VEC <= g.d;
   float res[VEC];
+  pdl_wait();        // PDL: order / status / rows are valid from here
   if (status != nullptr && *status != 0) {
 #pragma unroll
     for (int c = 0; c < VEC; ++c) res[c] = quiet_nan();
@@ -152,8 +155,8 @@ template <int N, int F>
 static void launch_static(const RowTable& rows, const Geom& g, const int32_t* order, const int32_t* status, float* out, cudaStream_t st) {
   if (g.nv <= 0) return;
   const unsigned blocks = (unsigned)((g.nv + kK4Threads - 1) / kK4Threads);
-  if (g.vec == 2) k4_bulyan_static<N, F, 2><<<blocks, kK4Threads, 0, st>>>(rows, g, order, status, out);
-  else            k4_bulyan_static<N, F, 1><<<blocks, kK4Threads, 0, st>>>(rows, g, order, status, out);
+  if (g.vec == 2) launch_after(k4_bulyan_static<N, F, 2>, blocks, kK4Threads, 0, st, rows, g, order, status, out);
+  else            launch_after(k4_bulyan_static<N, F, 1>, blocks, kK4Threads, 0, st, rows, g, order, status, out);
 }
 
 bool launch_bulyan_reduce_static(const RowTable& rows, int n, int f, int m, const int32_t* order, const int32_t* status,
@@ -173,8 +176,8 @@ static void launch_theta(const RowTable& rows, int64_t d, int n, int f, int m, c
   const int m_max = n - f - 2;
   const int rowsm = m_max > THETA ? m_max : THETA;
   const size_t smem = (size_t)rowsm * kK4Threads * sizeof(float);
-  k4_bulyan<THETA><<<(unsigned)((threads + kK4Threads - 1) / kK4Threads), kK4Threads, smem, st>>>(
-      rows, d, n, f, m, 1, -1, order, status, out);
+  launch_after(k4_bulyan<THETA>, (unsigned)((threads + kK4Threads - 1) / kK4Threads), kK4Threads, smem, st,
+               rows, d, n, f, m, 1, -1, order, status, out);
 }
 
 bool launch_bulyan_reduce(const RowTable& rows, int n, int f, int m, const int32_t* order, const int32_t* status,

@@ -6,6 +6,29 @@
 
 namespace bz {
 
+// Programmatic dependent launch (PDL): the kernel may be scheduled as soon as the CTAs of the
+// previous kernel of the stream have exited or triggered, instead of after the whole grid has
+// drained and the launch latency has been paid again; it MUST execute pdl_wait() before it
+// reads or writes anything global (the wait returns once the previous grid has completed and its
+// writes are visible).  Used for the second pass of the distance rules (K3 / K4 after K2 + scoring).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+template <class... Params, class... Args>
+inline cudaError_t launch_after(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, Params(args)...);
+}
+
 // Elements per thread in the aligned body of a K1 launch: 4 (LDG.128) while 4n values fit
 // the register file comfortably, else 2 (LDG.64).  The scalar variant (1) serves the
 // unaligned head/tail and rows whose alignments disagree.
