@@ -117,7 +117,7 @@ def make_rows(torch, n, d, device, seed, sets):
   gen = torch.Generator(device=device).manual_seed(seed)
   return [[torch.randn(d, device=device, generator=gen) for _ in range(n)] for _ in range(sets)]
 
-EXCHANGE = "nccl"
+EXCHANGE = "auto"
 
 def call_device(bz, sharded, gar, rows, f, world):
   """ One aggregation of device-resident rows (the step of the timed region). """
@@ -250,6 +250,107 @@ def run_reference(args):
               e2e=dict(value=value, unit="params/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
   print(json.dumps(line), flush=True)
 
+def timed_max_over_ranks(torch, dist, device, fn, steps, warmup=5):
+  """ µs per step of `fn(k)`: `steps` calls between two CUDA events on the current stream after a
+  barrier + synchronize, the MAX over the ranks (every rank issues the same collectives). """
+  for k in range(warmup):
+    fn(k)
+  if dist is not None:
+    dist.barrier()
+  torch.cuda.synchronize()
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  a.record()
+  for k in range(steps):
+    fn(k)
+  b.record()
+  torch.cuda.synchronize()
+  ms = a.elapsed_time(b)
+  if dist is not None:
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+  return ms / steps * 1e3
+
+def sharded_block(torch, dist, bz, sharded, device, world, rank, peak):
+  """ The multi-GPU path BASELINE.json's north_star names, timed on the device:
+    collective  Multi-Krum + Bulyan at C3 (n = 25, f = 5, d = 1,310,922 PER GPU: weak scaling)
+                through the prepared three-phase call, with the NCCL all-gather of the R
+                n x n blocks and with the blocks read in place over NVLink peer memory; beside
+                the same rule on one GPU without any exchange (engine.Plan) in the same process;
+    c4_strong   median + trimmed mean at C4 (n = 51, f = 12, d = 36,546,980 TOTAL, split over the
+                N ranks: strong scaling; no collective on this path). """
+  out = dict(world=world)
+  steps = 200
+  # ---- collective path, weak scaling --------------------------------------------------------------
+  n, f, d = 25, 5, 1_310_922
+  sets = 4                                           # 4 x 131 MB > 3 x L2
+  gen = torch.Generator(device=device).manual_seed(77 + rank)
+  stacks = [[torch.randn(d, device=device, generator=gen) for _ in range(n)] for _ in range(sets)]
+  rows = []
+  for gar in ("krum", "bulyan"):
+    rec = dict(gar=gar, n=n, f=f, d_per_gpu=d, steps=steps)
+    local = [bz.Plan(gar, st, f=f) for st in stacks]
+    rec["single_gpu_us"] = timed_max_over_ranks(torch, dist, device, lambda k: local[k % sets](), steps)
+    for exchange in ("nccl", "p2p"):
+      try:
+        plans = [sharded.ShardedPlan(gar, st, f=f, exchange=exchange) for st in stacks]
+        rec[exchange + "_us"] = timed_max_over_ranks(torch, dist, device, lambda k: plans[k % sets](), steps)
+        rec[exchange + "_vs_single"] = rec[exchange + "_us"] / rec["single_gpu_us"]
+        del plans
+      except Exception as err:
+        rec[exchange + "_error"] = f"{type(err).__name__}: {err}"[:200]
+    alg = (n + (n - f - 2) + 1) * d * 4
+    best = min(rec.get("nccl_us", math.inf), rec.get("p2p_us", math.inf))
+    if math.isfinite(best):
+      rec["aggregate_gbs"] = world * alg / (best * 1e-6) / 1e9
+      rec["hbm_frac_per_gpu"] = alg / (best * 1e-6) / 1e9 / peak
+    rows.append(rec)
+    del local
+  out["collective"] = dict(what="weak scaling: n=25 f=5 d=1,310,922 per GPU; one exchange of R blocks of n*n fp64 per step; us per step, max over ranks",
+                           exchange_bytes_per_rank=n * n * 8, rules=rows)
+  del stacks
+  torch.cuda.empty_cache()
+  # ---- C4, strong scaling ------------------------------------------------------------------------
+  n, f, total = 51, 12, 36_546_980
+  per = (total + world - 1) // world
+  d = min(per, total - rank * per)
+  sets = max(1, min(3, math.ceil(3 * L2_BYTES / (n * d * 4))))
+  gen = torch.Generator(device=device).manual_seed(177 + rank)
+  stacks = [[torch.randn(d, device=device, generator=gen) for _ in range(n)] for _ in range(sets)]
+  rows = []
+  for gar in ("median", "trmean"):
+    plans = [sharded.ShardedPlan(gar, st, f=f) for st in stacks]
+    us = timed_max_over_ranks(torch, dist, device, lambda k: plans[k % sets](), 20 if world == 1 else 50, warmup=3)
+    alg = (n + 1) * total * 4
+    rows.append(dict(gar=gar, n=n, f=f, d_total=total, d_this_rank=d, us_per_step=us, params_per_s=total / (us * 1e-6),
+                     aggregate_gbs=alg / (us * 1e-6) / 1e9, hbm_frac_per_gpu=alg / world / (us * 1e-6) / 1e9 / peak))
+    del plans
+  out["c4_strong"] = dict(what="strong scaling: n=51 f=12 d=36,546,980 split over the ranks (BASELINE.json configs[3]); us per step, max over ranks; speed-up = the N=1 line of the same run series / this",
+                          rules=rows)
+  del stacks
+  torch.cuda.empty_cache()
+  return out
+
+def h2d_probe(torch, device, nbytes):
+  """ Measured host->device rate of ONE contiguous pinned copy of the step's input size: the PCIe
+  floor of the e2e leg on this box. """
+  try:
+    host = torch.empty(nbytes // 4, dtype=torch.float32).pin_memory()
+    dst = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+    for _ in range(2):
+      dst.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+      dst.copy_(host, non_blocking=True)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 5
+    return dict(gbs=nbytes / (ms * 1e-3) / 1e9, ms=ms, bytes=nbytes)
+  except Exception as err:
+    return dict(error=str(err)[:120])
+
 def run_b200(args):
   import torch
   world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -284,8 +385,9 @@ def run_b200(args):
     step = lambda k: plans[k % sets]()
     api = f"byzantinemomentum_b200.Plan({gar!r}, rows, f={f})()"
   else:
-    step = lambda k: call_device(bz, sharded, gar, inputs[k % sets], f, world)
-    api = f"byzantinemomentum_b200.sharded.aggregate{'_p2p' if EXCHANGE == 'p2p' else ''}({gar!r}, rows, f={f})"
+    splans = [sharded.ShardedPlan(gar, rows, f=f, exchange=EXCHANGE) for rows in inputs]
+    step = lambda k: splans[k % sets]()
+    api = f"byzantinemomentum_b200.sharded.ShardedPlan({gar!r}, rows, f={f}, exchange={splans[0].exchange!r})()"
   for k in range(max(args.warmup, 3)):
     step(k)
   barrier()
@@ -356,7 +458,10 @@ def run_b200(args):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_total = float(t.item())
   e2e_ms = e2e_total / e2e_steps
+  probe = h2d_probe(torch, device, n * d * 4)
   e2e = dict(value=world * d / (e2e_ms * 1e-3), unit="params/s", h2d_bytes_per_step=n * d * 4, d2h_bytes_per_step=d * 4,
+             h2d_probe=probe, pcie_floor_ms=probe.get("ms"), h2d_rate_achieved_gbs=n * d * 4 / (e2e_ms * 1e-3) / 1e9,
+             note="pcie_floor_ms = one contiguous pinned 131 MB copy on THIS box (PCIe Gen5 x16 nominal: 2.1-2.4 ms); the step adds the kernel (~25 us), the 5 MB result copy and its synchronisation",
              ms_per_step=e2e_ms, steps=e2e_steps, host_buffers="pinned" + (", allocated on the GPU-local NUMA node" if numa_local else ""), call=f"byzantinemomentum_b200.gars[{gar!r}].unchecked(gradients=<{n} pinned host tensors>, f={f})")
   del host
 
@@ -388,6 +493,11 @@ def run_b200(args):
       line["torch_cuda_baseline"] = dict(error=str(err)[:200])
     if not args.no_sweep:
       line["sweep"] = sweep(torch, bz, device, peak)
+  if not args.no_sharded and (world > 1 or args.sharded):
+    try:
+      line["sharded"] = sharded_block(torch, dist, bz, sharded, device, world, rank, peak)
+    except Exception as err:
+      line["sharded"] = dict(error=f"{type(err).__name__}: {err}"[:300])
   if rank == 0:
     print(json.dumps(line), flush=True)
   if dist is not None:
@@ -400,7 +510,8 @@ def sweep(torch, bz, device, peak):
   full = ["average", "median", "trmean", "phocas", "meamed", "krum", "bulyan", "aksel", "cge"]
   short = ["median", "trmean", "krum", "bulyan"]
   # every rule at BASELINE.json's shapes, plus the d sweep at n = 25 (metric: "per GAR at n=25, d sweep")
-  plan = [(25, 10, 79_510, full), (25, 10, 1_310_922, full), (25, 10, 36_489_290, full), (11, 5, 79_510, full + ["brute"]),
+  c3 = ["krum", "bulyan", "aksel", "cge"]
+  plan = [(25, 5, 1_310_922, c3), (25, 5, 36_489_290, ["krum", "bulyan"]), (25, 10, 79_510, full), (25, 10, 1_310_922, full), (25, 10, 36_489_290, full), (11, 5, 79_510, full + ["brute"]),
           (11, 3, 1_310_922, full + ["brute"]), (51, 12, 4_568_373, full),
           (25, 10, 1 << 16, short), (25, 10, 431_080, short), (25, 10, 2_384_036, short), (25, 10, 1 << 23, short), (25, 10, 1 << 25, short)]
   for n, f, d, gars in plan:
@@ -477,7 +588,9 @@ def main():
   ap.add_argument("--nb-byz", dest="f", type=int, default=10)
   ap.add_argument("--dim", dest="d", type=int, default=1_310_922)
   ap.add_argument("--no-sweep", action="store_true")
-  ap.add_argument("--exchange", choices=("nccl", "p2p"), default="nccl",
+  ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the `sharded` block (collective path + C4 strong scaling)")
+  ap.add_argument("--sharded", action="store_true", help="N = 1: also run the `sharded` block (its N = 1 reference line)")
+  ap.add_argument("--exchange", choices=("auto", "nccl", "p2p"), default="auto",
                   help="N > 1, distance-based rules: all-gather (NCCL) or blocks read in place over NVLink peer memory")
   args = ap.parse_args()
   global EXCHANGE

@@ -370,21 +370,11 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
         for (int r = 0; r < C; ++r) mbar_arrive_remote(&empty[s], (unsigned)r);
     }
     if (task.kind != 0 && ++pending == kFlushTiles) { pending = 0; ring_flush(acc, lane, dacc); }
-    if (STAGES >= 3) {
-      // refill the stage released one iteration ago (every warp of the cluster is past it by now)
-      if (refiller && k >= 1 && issued < mine) {
-        mbar_wait(&empty[sp], pp);
-        refill(sp);
-        ++issued;
-      }
-    } else {
-      // two stages (large tiles of many rows): no slack to defer, refill this stage as soon as the
-      // whole cluster has released it
-      if (refiller && issued < mine) {
-        mbar_wait(&empty[s], parity);
-        refill(s);
-        ++issued;
-      }
+    // refill the stage released one iteration ago (every warp of the cluster is past it by now)
+    if (refiller && k >= 1 && issued < mine) {
+      mbar_wait(&empty[sp], pp);
+      refill(sp);
+      ++issued;
     }
     sp = s; pp = parity;
     if (++s == STAGES) { s = 0; parity ^= 1u; }
@@ -595,11 +585,7 @@ int launch_pairdist_ring(const RowTable& rows, int n, int64_t d, double* parts, 
     if (rows_alloc > 25) return -1;
     nparts = BZ_RING(512, 4, false);
   } else if (rows_alloc <= 35) nparts = BZ_RING(512, 3, true);
-  else {
-    const char* big = getenv("BYZAGG_K2_BIGTILE");
-    if (rows_alloc <= 55 && big && big[0] == '1') nparts = BZ_RING(512, 2, true);
-    else                                          nparts = BZ_RING(256, 3, true);
-  }
+  else                         nparts = BZ_RING(256, 3, true);   // (512-column tiles with 2 stages measured 20 % slower at n = 40...51)
 #undef BZ_RING
   if (select != nullptr) select->fused = (nparts > 0 && tail.kind != 0) ? 1 : 0;
   return nparts;

@@ -29,7 +29,7 @@ import torch.distributed as dist
 
 from . import engine as _engine
 
-__all__ = ["aggregate", "aggregate_p2p", "compute_avg_dev_max", "replicate", "PeerExchange", "COORDINATE_WISE", "DISTANCE_BASED"]
+__all__ = ["aggregate", "aggregate_p2p", "compute_avg_dev_max", "replicate", "PeerExchange", "ShardedPlan", "COORDINATE_WISE", "DISTANCE_BASED"]
 
 COORDINATE_WISE = ("average", "median", "trmean", "phocas", "meamed")
 DISTANCE_BASED = ("krum", "bulyan", "brute", "aksel", "cge")
@@ -122,6 +122,151 @@ def aggregate_p2p(gar, gradients, f=None, m=None, mode="mid", group=None, return
   else:
     raise KeyError(f"unknown aggregation rule {gar!r}")
   return (out, sel) if return_selection else out
+
+class ShardedPlan:
+  """ Prepared d-sharded aggregation (the multi-GPU counterpart of `engine.Plan`): every argument
+  of the three phases is resolved once — row pointers, this rank's partial block, the gathered
+  [R, n, n] buffer (or the peers' addresses of the symmetric slots), selection, output, workspace —
+  so that a step is 3 C-ABI calls plus ONE exchange, with no allocation and no host/device
+  synchronisation.  The rows and the output are held; their CONTENT may change between calls.
+
+      plan = sharded.ShardedPlan("krum", shard_rows, f=5)          # exchange="auto": peer memory when available
+      out_shard = plan()                                            # plan.out, plan.selection (device int32)
+
+  exchange: "nccl"  one `all_gather_into_tensor` of the R blocks (n*n*8 B each), then the selection
+                    kernel sums them in rank order;
+            "p2p"   the block is written straight into this rank's slot of a SYMMETRIC buffer, one
+                    device-side barrier, and the selection kernel reads the R blocks in place from
+                    the R peers over NVLink (`bz_*_select_peers`): gather + scoring in one kernel;
+            "auto"  "p2p" when symmetric memory can be set up for the group, else "nccl".
+  Both exchanges use the same fixed summation order: bitwise identical selections on every rank.
+  Coordinate-wise rules need no exchange and simply wrap `engine.Plan`. """
+  def __init__(self, gar, gradients, f=None, m=None, mode="mid", group=None, exchange="auto"):
+    import ctypes
+    from . import _lib
+    self.gar, self.group = gar, group
+    self.rows = list(gradients)
+    n = self.n = len(self.rows)
+    self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+    self.selection = None
+    self.status = None
+    if gar in COORDINATE_WISE:
+      self._local = _engine.Plan(gar, self.rows, f=f)
+      self.out = self._local.out
+      self.exchange = "none"
+      return
+    if gar not in DISTANCE_BASED:
+      raise KeyError(f"unknown aggregation rule {gar!r}")
+    self._local = None
+    lib = _lib.lib()
+    prep = _engine._prepare_device(self.rows)
+    if not all(g.is_contiguous() for g in self.rows):
+      raise ValueError("ShardedPlan takes contiguous rows")
+    device = self.device = prep.device
+    d = self.d = prep.d
+    self._ptrs = (ctypes.c_void_p * n)(*[g.data_ptr() for g in self.rows])
+    self._stream = prep.stream
+    self._ws = _engine._workspace(device, prep.stream)
+    ws, wn, st = self._ws.data_ptr(), self._ws.numel(), self._stream
+    self.out = torch.empty(d, dtype=torch.float32, device=device)
+    self._meta = torch.empty(n + 1, dtype=torch.int32, device=device)
+    meta, status = self._meta.data_ptr(), self._meta[n:].data_ptr()
+    self.selection = self._meta[:n]
+    o = self.out.data_ptr()
+    pair = gar in ("krum", "bulyan", "brute")
+    width = n * n if pair else n
+    # ---- exchange -------------------------------------------------------------------------------
+    if exchange == "auto":
+      exchange = "nccl"
+      if self.world > 1 and self.world <= _lib.MAX_PEERS:
+        try:
+          self._ex = peer_exchange(n, device, group)
+          exchange = "p2p"
+        except Exception:
+          exchange = "nccl"
+    elif exchange == "p2p":
+      self._ex = peer_exchange(n, device, group)
+    elif exchange != "nccl":
+      raise ValueError(f"unknown exchange {exchange!r}")
+    self.exchange = exchange
+    if exchange == "p2p":
+      ex = self._ex
+      # two slots -> two prepared argument sets; the step counter of the exchange picks one
+      self._slots = []
+      for slot in range(2):
+        off = slot * n * n
+        mine = ex.buffer[off:off + width]
+        table = (ctypes.c_void_p * self.world)(*[base + off * 8 for base in ex.peer_base])
+        self._slots.append((mine, table))
+    else:
+      self._part = torch.empty(width, dtype=torch.float64, device=device)
+      self._gathered = torch.empty((self.world, width), dtype=torch.float64, device=device)
+    # ---- phases ---------------------------------------------------------------------------------
+    if gar == "aksel":
+      self._center = torch.empty(d, dtype=torch.float32, device=device)
+      self._pre = (lib.bz_median, (self._ptrs, n, d, self._center.data_ptr(), st))
+      center = self._center.data_ptr()
+    else:
+      self._pre = None
+      center = None
+    def phase_a(part_ptr):
+      if pair:
+        return lib.bz_pairdist_partial, (self._ptrs, n, d, part_ptr, ws, wn, st)
+      return lib.bz_rowdist_partial, (self._ptrs, n, center, d, part_ptr, ws, wn, st)
+    def phase_b(parts_ptr, peers):
+      R = self.world
+      if gar == "krum":
+        return (lib.bz_krum_select_peers if peers else lib.bz_krum_select), (parts_ptr, R, n, int(f), meta, st)
+      if gar == "bulyan":
+        return (lib.bz_bulyan_select_peers if peers else lib.bz_bulyan_select), (parts_ptr, R, n, int(f), int(mm), meta, status, st)
+      if gar == "brute":
+        return (lib.bz_brute_select_peers if peers else lib.bz_brute_select), (parts_ptr, R, n, int(f), meta, status, st)
+      return (lib.bz_rowdist_select_peers if peers else lib.bz_rowdist_select), (parts_ptr, R, n, 1 if gar == "cge" else 0, meta, st)
+    mm = (n - f - 2 if m is None else m) if gar in ("krum", "bulyan") else None
+    if gar == "krum":
+      self._c = (lib.bz_average_selected, (self._ptrs, n, meta, int(mm), 1, float(mm), None, d, o, st))
+    elif gar == "bulyan":
+      self.status = self._meta[n:]
+      self._c = (lib.bz_bulyan_reduce, (self._ptrs, n, int(f), int(mm), meta, status, d, o, st))
+    elif gar == "brute":
+      self.status = self._meta[n:]
+      self.selection = self._meta[:n - int(f)]
+      self._c = (lib.bz_average_selected, (self._ptrs, n, meta, n - int(f), 1, float(n - int(f)), status, d, o, st))
+    elif gar == "aksel":
+      if mode not in _lib.AKSEL_MODES:
+        raise NotImplementedError(mode)
+      count = (n + 1) // 2 if mode == "mid" else n - int(f)
+      self._c = (lib.bz_average_selected, (self._ptrs, n, meta, count, 1, float(count), None, d, o, st))
+    else:  # cge
+      count = n - int(f)
+      self._c = (lib.bz_average_selected, (self._ptrs, n, meta, count, 0, float(count), None, d, o, st))
+    if exchange == "p2p":
+      self._ab = [(phase_a(mine.data_ptr()), phase_b(table, True)) for mine, table in self._slots]
+    else:
+      self._ab = [(phase_a(self._part.data_ptr()), phase_b(self._gathered.data_ptr(), False))]
+    self._check = _lib.check
+  def __call__(self):
+    if self._local is not None:
+      return self._local()
+    check = self._check
+    with _engine._on(self.device):
+      if self._pre is not None:
+        check(self._pre[0](*self._pre[1]), "bz_median")
+      if self.exchange == "p2p":
+        ex = self._ex
+        (fa, aa), (fb, ab) = self._ab[ex.step % 2]
+        check(fa(*aa), "phase A")
+        ex.publish()
+      else:
+        (fa, aa), (fb, ab) = self._ab[0]
+        check(fa(*aa), "phase A")
+        if self.world > 1:
+          dist.all_gather_into_tensor(self._gathered, self._part, group=self.group)
+        else:
+          self._gathered.copy_(self._part.unsqueeze(0))
+      check(fb(*ab), "phase B")
+      check(self._c[0](*self._c[1]), "phase C")
+    return self.out
 
 def aggregate(gar, gradients, f=None, m=None, mode="mid", group=None, backend=None, return_selection=False):
   """ Aggregate this rank's shard.

@@ -136,3 +136,34 @@ def test_plan_rejects_strided_rows_but_the_plain_call_packs_them():
     bz.Plan("median", columns)
   got = bz.gars["median"].unchecked(gradients=columns)
   parity.assert_bit_exact(got.cpu().numpy(), orc.median([c.cpu().numpy() for c in columns]), "median of strided views")
+
+@pytest.mark.parametrize("gar,kw", [("krum", dict(f=5)), ("krum", dict(f=5, m=3)), ("bulyan", dict(f=5)), ("aksel", dict(f=5)),
+                                    ("aksel", dict(f=5, mode="n-f")), ("cge", dict(f=5)), ("median", dict(f=5)), ("trmean", dict(f=5)), ("average", {})])
+def test_sharded_plan_on_one_rank_equals_the_plain_call(gar, kw):
+  """ `sharded.ShardedPlan` (the prepared three-phase call) without a process group = world of 1:
+  the all-gather degenerates to a copy, everything else is the code path of the ranks.  Must
+  reproduce the single-device rule bit for bit (same kernels, same selection), call after call,
+  and follow in-place updates of the rows. """
+  import byzantinemomentum_b200 as bz
+  from byzantinemomentum_b200 import sharded
+  n, nb, d = 25, 5, 20011
+  rows = [r.to(DEV) for r in _inputs(n, nb, d, 91)]
+  plan = sharded.ShardedPlan(gar, rows, **kw)
+  want = bz.gars[gar](gradients=rows, **({"f": 5} | kw))
+  for _ in range(3):
+    got = plan()
+  assert torch.equal(got, want) or gar == "bulyan" and torch.allclose(got, want, rtol=0, atol=0)
+  if gar in ("krum", "aksel", "cge"):
+    assert plan.selection.cpu().tolist() == bz.last_selection()
+  rows[0].mul_(3.)                       # content changes, pointers do not
+  want = bz.gars[gar](gradients=rows, **({"f": 5} | kw))
+  assert torch.equal(plan(), want)
+
+def test_sharded_plan_brute_and_status():
+  import byzantinemomentum_b200 as bz
+  from byzantinemomentum_b200 import sharded
+  rows = [r.to(DEV) for r in _inputs(11, 3, 5003, 92)]
+  plan = sharded.ShardedPlan("brute", rows, f=3)
+  want = bz.gars["brute"](gradients=rows, f=3)
+  assert torch.equal(plan(), want) and int(plan.status.item()) == 0
+  assert plan.selection.cpu().tolist() == bz.last_selection()
