@@ -50,6 +50,9 @@ SIGNATURES = {
   "bz_krum": (_i, [_c_rows, _i, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
   "bz_bulyan": (_i, [_c_rows, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
   "bz_brute": (_i, [_c_rows, _i, _i, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+  "bz_krum_reuse": (_i, [_c_rows, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+  "bz_bulyan_reuse": (_i, [_c_rows, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+  "bz_brute_reuse": (_i, [_c_rows, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
   "bz_aksel": (_i, [_c_rows, _i, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
   "bz_cge": (_i, [_c_rows, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
   "bz_pairdist_partial": (_i, [_c_rows, _i, _i64, _vp, _vp, _sz, _vp]),
@@ -63,6 +66,7 @@ SIGNATURES = {
   "bz_brute_select_peers": (_i, [_c_rows, _i, _i, _i, _vp, _vp, _vp]),
   "bz_rowdist_select_peers": (_i, [_c_rows, _i, _i, _i, _vp, _vp]),
   "bz_avg_dev_max": (_i, [_c_rows, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
+  "bz_gradient_row": (_i, [_vp, _i64, _dbl, _vp, _i, _vp, _dbl, _dbl, _vp, _vp, _sz, _vp]),
   "bz_average_selected": (_i, [_c_rows, _i, _vp, _i, _i, _dbl, _vp, _i64, _vp, _vp]),
   "bz_bulyan_reduce": (_i, [_c_rows, _i, _i, _i, _vp, _vp, _i64, _vp, _vp]),
 }

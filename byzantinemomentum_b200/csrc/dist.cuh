@@ -45,7 +45,15 @@ struct SelectTail {
   int32_t* order;
   int32_t* status;
   unsigned* ticket;         // 128 bytes of device scratch
-  int fused;
+  int fused;                // out: the pass ran the step
+  // distance reuse (optional): old_index[i] = position of ORIGINAL row i in the table of squared
+  // distances a previous call left in `cache_in` (u_old x u_old doubles), or -1; the table of this
+  // call is written to `cache_out` (u x u).  `reused` is set when only the new rows' pairs were computed.
+  const int32_t* old_index;
+  const double* cache_in;
+  int u_old;
+  double* cache_out;
+  int reused;
 };
 int launch_pairdist_ring(const RowTable& rows, int n, int64_t d, double* parts, cudaStream_t st,
                          const unsigned char* self_rows, int nself, SelectTail* select = nullptr);
@@ -55,8 +63,11 @@ int launch_pairdist_auto(const RowTable& rows, int u, int64_t d, double* parts, 
                          const int* to_unique, int n_orig, SelectTail* select = nullptr);
 
 // K2': parts[x*n + i] = share of sum_k (rows[i][k] - center[k])^2 (center NULL: the origin).
+// order != NULL: the last CTA also sums the blocks and writes the stable order of the n keys
+// (sqrt_norm as in bz_rowdist_select) — the selection step without its launch; `ticket`: one zeroed word.
 int launch_rowdist(const RowTable& rows, int n, const float* const* host_rows, const float* center, int64_t d,
-                   double* parts, cudaStream_t st, int reverse = 0);
+                   double* parts, cudaStream_t st, int reverse = 0, int32_t* order = nullptr, unsigned* ticket = nullptr,
+                   int sqrt_norm = 0);
 
 // ---- K6: study metrics in one pass (k6_study.cu) -------------------------------------------------
 // avg = (rows[0] + rows[1] + ...)/n; stats[0] = sum avg^2, stats[1] = max |avg|,

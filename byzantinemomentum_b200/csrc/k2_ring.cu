@@ -69,6 +69,22 @@ struct RingTail {
   int32_t* status;
   unsigned* ticket;         // kTailTickets words, zero before the launch; left at zero
   RowMap map;               // original rows -> unique rows
+  // Distance reuse (the attacks' line search, attacks/identical.py:68-77: the same honest rows with a
+  // new Byzantine row at every evaluation): `old_index[k]` >= 0 places unique row k in the table of
+  // a previous call (`cache_in`, u_old x u_old); pairs of two such rows are taken from it, the pass
+  // only computes the pairs of the NEW rows (star tasks).  The assembled table goes to `cache_out`.
+  const double* cache_in;
+  double* cache_out;
+  int u_old;
+  signed char old_index[kMaxN];
+};
+
+// New rows of a reuse call: star task = one new row against 25 consecutive rows.
+constexpr int kStarMax = 4;
+struct StarList {
+  unsigned char row[kStarMax];
+  int count;                // 0: the ordinary pass over all pairs
+  int slots;                // rows per star task: 3 or 25
 };
 
 // ---- cluster helpers -------------------------------------------------------------------------
@@ -93,8 +109,8 @@ __device__ __forceinline__ void mbar_arrive_remote(unsigned long long* bar, unsi
 // composite 2k covers diagonal blocks 5k, 5k+1 (whole) and the identity 5-cycle of 5k+2,
 // composite 2k+1 covers 5k+3, 5k+4 (whole) and the second 5-cycle of 5k+2.
 struct Task {
-  int kind;        // 0 = none, 1 = OFF, 2 = COMP
-  int g0, g1, g2;  // OFF: (ga, gb, -); COMP: (X, Y, Z) group indices, -1 = absent
+  int kind;        // 0 = none, 1 = OFF, 2 = COMP, 3 = STAR
+  int g0, g1, g2;  // OFF: (ga, gb, -); COMP: (X, Y, Z) group indices, -1 = absent; STAR: (pivot row, first group, -)
   int perm;        // COMP: Z rows walked in the order 0,2,4,1,3
 };
 __host__ __device__ inline int ring_ncomp(int ng) {
@@ -213,6 +229,27 @@ __device__ __forceinline__ void sweep_comp(const float* x_base, const float* y_b
   }
 }
 
+// STAR: the pivot row against NS consecutive rows (NS = 3: a new row's pairs spread over many warps, so
+// that a reuse pass is bound by the staging of the rows, not by one warp's 25 pairs; NS = 25 when there
+// are too few warps for that).  Each pair goes through exactly the operations it goes through in an
+// OFF / COMP task — same lane, same steps, (a-b)^2 = (b-a)^2 bit for bit — so a distance computed here
+// equals the one the full pass would produce.  Slots past `valid` re-read the first row (in bounds).
+template <int T, int NS>
+__device__ __forceinline__ void sweep_star(const float* x_base, const float* r_base, int valid, int lane, u64 (&acc)[kRSlots]) {
+#pragma unroll
+  for (int c = 0; c < T; c += 128) {
+    const int o = c + lane * 4;
+    const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(x_base + o);
+#pragma unroll
+    for (int p = 0; p < NS; ++p) {
+      const ulonglong2 r = *reinterpret_cast<const ulonglong2*>(r_base + (p < valid ? p : 0) * T + o);
+      const u64 d0 = sub2(x.x, r.x), d1 = sub2(x.y, r.y);
+      acc[p] = fma2(d0, d0, acc[p]);
+      acc[p] = fma2(d1, d1, acc[p]);
+    }
+  }
+}
+
 template <int T>
 __device__ __forceinline__ void sweep_self(const float* stage, const int (&srow)[kSelfPerWarp], int nself, int lane, u64 (&facc)[kSelfPerWarp]) {
 #pragma unroll
@@ -258,7 +295,8 @@ __device__ __forceinline__ void ring_stage_tail(float* buf, const RowTable& rows
 template <int T, int STAGES, bool SELF, bool CLUSTER>
 __global__ void __launch_bounds__(kRThreads, 1)
 k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList self, const __grid_constant__ RingTail tail,
-        const int n, const int csize, const int64_t d, const int64_t nfull, double* __restrict__ parts) {
+        const __grid_constant__ StarList star, const int n, const int csize, const int64_t d, const int64_t nfull,
+        double* __restrict__ parts) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ng = (n + kG - 1) / kG;
@@ -272,7 +310,15 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
   const int cluster_id = CLUSTER ? (int)(blockIdx.x / C) : (int)blockIdx.x;
   const int nclusters = CLUSTER ? (int)(gridDim.x / C) : (int)gridDim.x;
 
-  const Task task = make_task(rank * kRWarps + warp, ng);
+  Task task;
+  if (star.count == 0) {
+    task = make_task(rank * kRWarps + warp, ng);
+  } else {
+    // reuse call: star task t = (new row t / chunks, rows [slots (t % chunks), + slots)); g1 = first ROW here
+    const int chunks = (n + star.slots - 1) / star.slots, t = rank * kRWarps + warp;
+    task = Task{0, -1, -1, -1, 0};
+    if (t < star.count * chunks) { task.kind = 3; task.g0 = star.row[t / chunks]; task.g1 = (t % chunks) * star.slots; }
+  }
   // Rows this warp brings in: global issue slot q = r mod (12 C) -> CTA q mod C, warp q / C
   const int slot = warp * C + rank;
   const int stride = kRWarps * C;
@@ -344,8 +390,9 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
       if (gw + q * kRWarps * C < self.count) { srow[q] = self.row[gw + q * kRWarps * C]; nself = q + 1; }
   }
   // shared-memory offsets of the task's row groups (absent groups read group 0: discarded)
-  const int o0 = (task.g0 >= 0 ? task.g0 : 0) * kG * T;
-  const int o1 = (task.g1 >= 0 ? task.g1 : 0) * kG * T;
+  const int o0 = task.kind == 3 ? task.g0 * T : (task.g0 >= 0 ? task.g0 : 0) * kG * T;
+  const int o1 = task.kind == 3 ? task.g1 * T : (task.g1 >= 0 ? task.g1 : 0) * kG * T;
+  const int star_valid = task.kind == 3 ? min(star.slots, n - task.g1) : 0;
   const int o2 = (task.g2 >= 0 ? task.g2 : 0) * kG * T;
   // fp32 terms per accumulator half between two flushes into fp64 (a tile adds T / 64 of them)
   constexpr int kFlushTiles = (BZ_K2_FLUSH_TERMS * 64) / T;
@@ -359,6 +406,10 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
     const float* buf = stages + (size_t)s * stage_floats;
     if (task.kind == 1)      sweep_off<T>(buf + o0, buf + o1, lane, acc);
     else if (task.kind == 2) sweep_comp<T>(buf + o0, buf + o1, buf + o2, task.perm, lane, acc);
+    else if (task.kind == 3) {
+      if (star.slots == 3) sweep_star<T, 3>(buf + o0, buf + o1, star_valid, lane, acc);
+      else                 sweep_star<T, kRSlots>(buf + o0, buf + o1, star_valid, lane, acc);
+    }
     if (SELF && nself > 0) sweep_self<T>(buf, srow, nself, lane, facc);
     __syncwarp();
     if (lane == 0) {
@@ -390,6 +441,10 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
     __syncthreads();
     if (task.kind == 1)      sweep_off<T>(stages + o0, stages + o1, lane, acc);
     else if (task.kind == 2) sweep_comp<T>(stages + o0, stages + o1, stages + o2, task.perm, lane, acc);
+    else if (task.kind == 3) {
+      if (star.slots == 3) sweep_star<T, 3>(stages + o0, stages + o1, star_valid, lane, acc);
+      else                 sweep_star<T, kRSlots>(stages + o0, stages + o1, star_valid, lane, acc);
+    }
     if (SELF && nself > 0) sweep_self<T>(stages, srow, nself, lane, facc);
     pending = 1;
   }
@@ -418,6 +473,10 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
       const int ri = g * kG + i, rj = g * kG + j;
       if (ri < n && rj < n) block[(size_t)ri * n + rj] = dacc;
     }
+  }
+  else if (task.kind == 3) {
+    const int r = task.g1 + lane;
+    if (lane < star_valid && r != task.g0) block[(size_t)min(r, task.g0) * n + max(r, task.g0)] = dacc;
   }
   if (SELF) {
 #pragma unroll
@@ -466,7 +525,6 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
       if (elected) {
         __threadfence();
         double* sm = reinterpret_cast<double*>(smem_raw);
-        const StridedParts all{gblocks, (size_t)len};
         if (tail.kind == 4) {
           // phase A of the d-sharded path: this rank's reduced block (entries outside i < j are 0)
           double* out_block = reinterpret_cast<double*>(tail.order);
@@ -475,10 +533,31 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
             for (int g = 0; g < ngroups; ++g) sum += __ldcg(gblocks + (size_t)g * len + e);
             out_block[e] = (e / n < e % n) ? sum : 0.;
           }
+        } else {
+          // The summed u x u table, group blocks added in index order (canonical: a pair has the same
+          // bits whether it comes out of a full pass, a star pass or the cache), assembled where the
+          // scoring code expects it; diagonal entries (alias flags) always come from this pass.
+          const int N = tail.n;
+          double* table = sm + (n == N ? 0 : (size_t)N * N);
+          for (int e = threadIdx.x; e < len; e += kRThreads) {
+            const int i = e / n, j = e - i * n;
+            double v = 0.;
+            if (i <= j) {
+              const int oi = tail.old_index[i], oj = tail.old_index[j];
+              if (i < j && tail.cache_in != nullptr && oi >= 0 && oj >= 0) {
+                v = __ldcg(tail.cache_in + (size_t)min(oi, oj) * tail.u_old + max(oi, oj));
+              } else {
+                for (int g = 0; g < ngroups; ++g) v += __ldcg(gblocks + (size_t)g * len + e);
+              }
+            }
+            table[e] = v;
+            if (tail.cache_out != nullptr) tail.cache_out[e] = v;
+          }
+          __syncthreads();
+          if (tail.kind == 3) brute_from_table(tail.map, N, tail.f, tail.total, tail.order, tail.status, sm);
+          else                score_from_table(tail.map, N, tail.count, tail.order, tail.kind == 2 ? tail.status : nullptr,
+                                               tail.f, tail.m, tail.kind == 2 ? 1 : 0, sm);
         }
-        else if (tail.kind == 3) brute_select_body(all, tail.map, ngroups, tail.n, tail.f, tail.total, tail.order, tail.status, tail.slices, sm);
-        else                score_select_body(all, tail.map, ngroups, tail.n, tail.count, tail.order, tail.kind == 2 ? tail.status : nullptr,
-                                              tail.f, tail.m, tail.kind == 2 ? 1 : 0, tail.slices, sm);
         if (threadIdx.x <= ngroups) tail.ticket[threadIdx.x] = 0u;
       }
     }
@@ -489,7 +568,8 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
 // ---- host side -------------------------------------------------------------------------------
 
 template <int T, int STAGES, bool SELF, bool CLUSTER>
-static int launch_ring_cfg(const RowTable& rows, const SelfList& self, RingTail& tail, int n, int C, int64_t d, double* parts, cudaStream_t st) {
+static int launch_ring_cfg(const RowTable& rows, const SelfList& self, RingTail& tail, const StarList& star, int n, int C, int64_t d,
+                           double* parts, cudaStream_t st) {
   const int ng = (n + kG - 1) / kG;
   const size_t smem = (size_t)STAGES * ng * kG * T * sizeof(float) + 2 * STAGES * sizeof(unsigned long long);
   auto kernel = k2_ring<T, STAGES, SELF, CLUSTER>;
@@ -536,14 +616,11 @@ static int launch_ring_cfg(const RowTable& rows, const SelfList& self, RingTail&
     const size_t nn = (size_t)tail.n * tail.n * sizeof(double);
     const size_t fixed = tail.kind == 3 ? nn + (size_t)(tail.n + 1) * (tail.n + 1) * sizeof(unsigned long long) + 64 * sizeof(double)
                                         : 2 * nn + (size_t)tail.n * sizeof(double);
-    if (tail.kind != 4 && avail < fixed + nn) tail.kind = 0;     // does not fit: the caller launches K5 itself
-    else {
-      const int ngroups = (nclusters + kTailGroup - 1) / kTailGroup;
-      tail.slices = tail.kind == 4 ? 1 : pick_slices(tail.n, ngroups, kRThreads, avail - fixed);
-      cudaMemsetAsync(tail.ticket, 0, kTailTickets * sizeof(unsigned), st);
-    }
+    if (tail.kind != 4 && avail < fixed) tail.kind = 0;          // does not fit: the caller launches K5 itself
+    else cudaMemsetAsync(tail.ticket, 0, kTailTickets * sizeof(unsigned), st);
   }
-  if (cudaLaunchKernelEx(&cfg, kernel, rows, self, tail, n, C, d, nfull, parts) != cudaSuccess) return -1;
+  if (tail.kind == 0 && star.count > 0) return -1;               // a star pass is only meaningful with the fused tail
+  if (cudaLaunchKernelEx(&cfg, kernel, rows, self, tail, star, n, C, d, nfull, parts) != cudaSuccess) return -1;
   return nclusters;
 }
 
@@ -573,13 +650,51 @@ int launch_pairdist_ring(const RowTable& rows, int n, int64_t d, double* parts, 
   const int rows_alloc = ng * kG;
   const bool selfk = nself > 0;
   RingTail tail = {};
+  StarList star = {};
+  for (int k = 0; k < kMaxN; ++k) tail.old_index[k] = -1;
   const char* nofuse = getenv("BYZAGG_K2_NOFUSE");
   if (select != nullptr && select->kind != 0 && !(nofuse && nofuse[0] == '1')) {
     tail.kind = select->kind; tail.n = select->n; tail.f = select->f; tail.m = select->m; tail.count = select->count;
     tail.total = select->total; tail.order = select->order; tail.status = select->status; tail.ticket = select->ticket;
     tail.map = make_map(select->to_unique, select->n, n);
+    tail.cache_out = select->cache_out;
+    tail.u_old = select->u_old;
+    select->reused = 0;
+    // Distance reuse: unique row k was row old_index[k] of the table in `cache_in`.  A star pass is
+    // taken when 1..kStarMax unique rows are new, every other one is in the table, and that table
+    // came out of the same launch geometry (tile width, cluster size: functions of the row count) —
+    // then every pair has the bits the full pass would give it.
+    if (select->cache_in != nullptr && select->old_index != nullptr && select->u_old >= 1 && select->kind != 4 && force_cluster == 0) {
+      int fresh[kMaxN], nfresh = 0;
+      bool ok = true;
+      for (int k = 0; k < n; ++k) {
+        int oi = -1;
+        for (int i = 0; i < select->n; ++i)
+          if ((select->to_unique ? select->to_unique[i] : i) == k) { oi = select->old_index[i]; break; }
+        if (oi >= select->u_old) ok = false;
+        tail.old_index[k] = (signed char)oi;
+        if (oi < 0) fresh[nfresh++] = k;
+      }
+      const int old_ng = (select->u_old + kG - 1) / kG, old_alloc = old_ng * kG;
+      const auto geometry = [](int alloc, int c) { return c == 1 ? 0 : alloc <= 35 ? 1 : 2; };
+      // 3 rows per star task when the cluster has the warps for it, else 25
+      int slots = 3;
+      if (nfresh * ((n + slots - 1) / slots) > kRWarps * C) slots = kRSlots;
+      const int chunks = (n + slots - 1) / slots;
+      ok = ok && nfresh >= 1 && nfresh <= kStarMax && nfresh * chunks <= kRWarps * C && nfresh < n
+              && ring_cluster_size(select->u_old) == C && geometry(old_alloc, C) == geometry(rows_alloc, C);
+      if (ok) {
+        star.count = nfresh;
+        star.slots = slots;
+        for (int q = 0; q < nfresh; ++q) star.row[q] = (unsigned char)fresh[q];
+        tail.cache_in = select->cache_in;
+        select->reused = 1;
+      } else {
+        for (int k = 0; k < kMaxN; ++k) tail.old_index[k] = -1;
+      }
+    }
   }
-#define BZ_RING(T, S, CL) (selfk ? launch_ring_cfg<T, S, true, CL>(rows, self, tail, n, C, d, parts, st) : launch_ring_cfg<T, S, false, CL>(rows, self, tail, n, C, d, parts, st))
+#define BZ_RING(T, S, CL) (selfk ? launch_ring_cfg<T, S, true, CL>(rows, self, tail, star, n, C, d, parts, st) : launch_ring_cfg<T, S, false, CL>(rows, self, tail, star, n, C, d, parts, st))
   int nparts;
   if (C == 1) {
     if (rows_alloc > 25) return -1;
@@ -587,7 +702,10 @@ int launch_pairdist_ring(const RowTable& rows, int n, int64_t d, double* parts, 
   } else if (rows_alloc <= 35) nparts = BZ_RING(512, 3, true);
   else                         nparts = BZ_RING(256, 3, true);   // (512-column tiles with 2 stages measured 20 % slower at n = 40...51)
 #undef BZ_RING
-  if (select != nullptr) select->fused = (nparts > 0 && tail.kind != 0) ? 1 : 0;
+  if (select != nullptr) {
+    select->fused = (nparts > 0 && tail.kind != 0) ? 1 : 0;
+    if (!select->fused) select->reused = 0;
+  }
   return nparts;
 }
 

@@ -11,6 +11,7 @@
 // summed by K5.  Deterministic; identical rows give identical sums.
 // Roofline: HBM, n·4 B per coordinate (+4 B for the centre).
 #include "dist.cuh"
+#include "k5_device.cuh"
 #include "reduce.cuh"
 
 namespace bz {
@@ -23,7 +24,7 @@ constexpr int kRdFlush = 8;      // vectors between two flushes
 template <bool CENTER, int VEC>
 __global__ void __launch_bounds__(kRdThreads, 2)
 k2_rowdist(const __grid_constant__ RowTable rows, const int n, const float* __restrict__ center, const Geom g,
-           double* __restrict__ parts) {
+           double* __restrict__ parts, int32_t* __restrict__ order, unsigned* __restrict__ ticket, const int sqrt_norm) {
   __shared__ double warp_tot[kRdWarps][kMaxN];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float acc[kMaxN];
@@ -101,11 +102,55 @@ k2_rowdist(const __grid_constant__ RowTable rows, const int n, const float* __re
     for (int w = 0; w < kRdWarps; ++w) s += warp_tot[w][threadIdx.x];
     parts[(size_t)blockIdx.x * n + threadIdx.x] = s;
   }
+  if (order == nullptr) return;
+  // The selection step (aksel.py:49 / cge.py:38: stable order of the n keys) in the LAST CTA to
+  // finish instead of a single-CTA launch: blocks summed in S interleaved classes with every load in
+  // flight, class sums added in class order (fixed for a given grid), keys as in k5_rowdist_select.
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double* partial = &warp_tot[0][0];                // S * n <= 256 doubles
+  double* key = partial + kRdThreads;               // n <= 64 doubles behind them (the table holds 512)
+  const int S = kRdThreads / n;
+  const int c = threadIdx.x % n, cls = threadIdx.x / n;
+  if (cls < S) {
+    double sum = 0.;
+    int p = cls;
+    for (; p + 7 * S < (int)gridDim.x; p += 8 * S) {
+      double t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = __ldcg(parts + (size_t)(p + u * S) * n + c);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) sum += t[u];
+    }
+    for (; p < (int)gridDim.x; p += S) sum += __ldcg(parts + (size_t)p * n + c);
+    partial[cls * n + c] = sum;
+  }
+  __syncthreads();
+  if (threadIdx.x < n) {
+    double sum = 0.;
+    for (int k = 0; k < S; ++k) sum += partial[k * n + threadIdx.x];
+    double v;
+    if (sqrt_norm) {
+      v = (double)(float)sqrt(sum);                  // cge.py:36-37: fp32 norm, non-finite -> +inf
+      if (!finite_d(v)) v = CUDART_INF;
+    } else {
+      v = (double)(float)sum;                        // aksel.py:41: fp32 sum of squares
+    }
+    key[threadIdx.x] = v;
+  }
+  __syncthreads();
+  stable_order(key, n, order);
+  if (threadIdx.x == 0) *ticket = 0u;
 }
 
 
 int launch_rowdist(const RowTable& rows, int n, const float* const* host_rows, const float* center, int64_t d,
-                   double* parts, cudaStream_t st, int reverse) {
+                   double* parts, cudaStream_t st, int reverse, int32_t* order, unsigned* ticket, int sqrt_norm) {
   // The centre doubles as the alignment reference ("out") of the geometry
   Geom g = make_geom(host_rows, n, center ? (const void*)center : (const void*)host_rows[0], nullptr, d, 4);
   g.reverse = reverse;
@@ -114,12 +159,13 @@ int launch_rowdist(const RowTable& rows, int n, const float* const* host_rows, c
   if (grid > cap) grid = cap;
   if (grid > kMaxParts) grid = kMaxParts;
   if (grid < 1) grid = 1;
+  if (order != nullptr) cudaMemsetAsync(ticket, 0, sizeof(unsigned), st);
   if (g.vec == 4) {
-    if (center) k2_rowdist<true, 4><<<(unsigned)grid, kRdThreads, 0, st>>>(rows, n, center, g, parts);
-    else        k2_rowdist<false, 4><<<(unsigned)grid, kRdThreads, 0, st>>>(rows, n, center, g, parts);
+    if (center) k2_rowdist<true, 4><<<(unsigned)grid, kRdThreads, 0, st>>>(rows, n, center, g, parts, order, ticket, sqrt_norm);
+    else        k2_rowdist<false, 4><<<(unsigned)grid, kRdThreads, 0, st>>>(rows, n, center, g, parts, order, ticket, sqrt_norm);
   } else {
-    if (center) k2_rowdist<true, 1><<<(unsigned)grid, kRdThreads, 0, st>>>(rows, n, center, g, parts);
-    else        k2_rowdist<false, 1><<<(unsigned)grid, kRdThreads, 0, st>>>(rows, n, center, g, parts);
+    if (center) k2_rowdist<true, 1><<<(unsigned)grid, kRdThreads, 0, st>>>(rows, n, center, g, parts, order, ticket, sqrt_norm);
+    else        k2_rowdist<false, 1><<<(unsigned)grid, kRdThreads, 0, st>>>(rows, n, center, g, parts, order, ticket, sqrt_norm);
   }
   return (int)grid;
 }

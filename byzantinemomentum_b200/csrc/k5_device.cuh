@@ -174,21 +174,15 @@ __device__ inline void stable_order(const double* key, int n, int32_t* __restric
 // row INCLUDING its +inf diagonal).  Putting +inf on the diagonal serves both: the extra +inf
 // can only be reached after every finite distance, where the sum is +inf either way.
 // Block-wide, any blockDim.x that `slices` divides; `sm`: (2 n^2 + n + slices n^2) doubles of shared memory.
-template <class Parts>
-__device__ void score_select_body(const Parts& parts, const RowMap& map, int nparts, int n, int count,
-                                  int32_t* __restrict__ order, int32_t* __restrict__ status, int f, int m, int bulyan, int slices,
-                                  double* sm) {
+// Scoring from an already summed table of squared distances, left by the caller in shared memory:
+// at `sm` (n x n) when map.u == n, else the u x u table at `sm + n*n`.  `sm`: (2 n^2 + n) doubles.
+__device__ inline void score_from_table(const RowMap& map, int n, int count, int32_t* __restrict__ order, int32_t* __restrict__ status,
+                                        int f, int m, int bulyan, double* sm) {
   double* dist = sm;
   double* sorted = sm + n * n;
   double* score = sm + 2 * n * n;
-  double* scratch = score + n;
-  if (map.u == n) {
-    block_sum_parts(parts, nparts, n * n, slices, scratch, dist);
-    finish_distances(dist, n, true, CUDART_INF, dist);
-  } else {
-    block_sum_parts(parts, nparts, map.u * map.u, slices, scratch, sorted);   // u x u table, parked in `sorted`
-    finish_distances_mapped(sorted, map, n, true, CUDART_INF, dist);
-  }
+  if (map.u == n) finish_distances(dist, n, true, CUDART_INF, dist);
+  else            finish_distances_mapped(sorted, map, n, true, CUDART_INF, dist);
   sort_rows(dist, sorted, n);
   for (int i = threadIdx.x; i < n; i += blockDim.x) score[i] = py_sum(sorted + i * n, count);
   __syncthreads();
@@ -211,6 +205,16 @@ __device__ void score_select_body(const Parts& parts, const RowMap& map, int npa
   }
 }
 
+template <class Parts>
+__device__ void score_select_body(const Parts& parts, const RowMap& map, int nparts, int n, int count,
+                                  int32_t* __restrict__ order, int32_t* __restrict__ status, int f, int m, int bulyan, int slices,
+                                  double* sm) {
+  double* scratch = sm + 2 * n * n + n;
+  if (map.u == n) block_sum_parts(parts, nparts, n * n, slices, scratch, sm);
+  else            block_sum_parts(parts, nparts, map.u * map.u, slices, scratch, sm + n * n);   // u x u table, parked in `sorted`
+  score_from_table(map, n, count, order, status, f, m, bulyan, sm);
+}
+
 
 // ---- brute: exhaustive minimum-diameter subset (brute.py:47-68) -----------------------------
 // Thread t scans a contiguous range of lexicographic ranks; the first strict minimum wins,
@@ -220,27 +224,19 @@ __device__ __forceinline__ unsigned long long sat_add(unsigned long long a, unsi
   return s < a ? ~0ull : s;
 }
 
-// Block-wide, any blockDim.x <= 1024 that `slices` divides; `sm`: n^2 + (n+1)^2 + slices n^2 + 64 doubles.
-template <class Parts>
-__device__ void brute_select_body(const Parts& parts, const RowMap& map, int nparts, int n, int f,
-                                  unsigned long long total, int32_t* __restrict__ sel, int32_t* __restrict__ status, int slices,
-                                  double* sm) {
+// Exhaustive search from an already summed table: at `sm` (n x n) when map.u == n, else the u x u
+// table at `sm + n*n` (where the Pascal triangle goes next).  `sm`: n^2 + (n+1)^2 + 64 doubles.
+__device__ inline void brute_from_table(const RowMap& map, int n, int f, unsigned long long total,
+                                        int32_t* __restrict__ sel, int32_t* __restrict__ status, double* sm) {
   double* dist = sm;                                                  // n*n
   unsigned long long* binom = reinterpret_cast<unsigned long long*>(sm + n * n);   // (n+1)*(n+1)
-  double* scratch = sm + n * n + (n + 1) * (n + 1);
-  // per-warp winners: behind the part-sum scratch (32 + 32 words)
-  double* best_diam = scratch + (size_t)slices * n * n;
+  // per-warp winners (32 + 32 words)
+  double* best_diam = sm + n * n + (n + 1) * (n + 1);
   unsigned long long* best_rank = reinterpret_cast<unsigned long long*>(best_diam + 32);
   const int k = n - f;
   const int W = n + 1;
-  if (map.u == n) {
-    block_sum_parts(parts, nparts, n * n, slices, scratch, dist);
-    finish_distances(dist, n, false, 0., dist);
-  } else {
-    double* table = reinterpret_cast<double*>(binom);        // u x u table, parked where the Pascal triangle goes next
-    block_sum_parts(parts, nparts, map.u * map.u, slices, scratch, table);
-    finish_distances_mapped(table, map, n, false, 0., dist);
-  }
+  if (map.u == n) finish_distances(dist, n, false, 0., dist);
+  else            finish_distances_mapped(reinterpret_cast<double*>(binom), map, n, false, 0., dist);
   // Pascal triangle, row by row
   for (int a = 0; a <= n; ++a) {
     for (int b = threadIdx.x; b <= n; b += blockDim.x) {
@@ -331,6 +327,17 @@ __device__ void brute_select_body(const Parts& parts, const RowMap& map, int npa
   }
 }
 
+
+// Block-wide, any blockDim.x <= 1024 that `slices` divides; `sm`: n^2 + (n+1)^2 + 64 + slices n^2 doubles.
+template <class Parts>
+__device__ void brute_select_body(const Parts& parts, const RowMap& map, int nparts, int n, int f,
+                                  unsigned long long total, int32_t* __restrict__ sel, int32_t* __restrict__ status, int slices,
+                                  double* sm) {
+  double* scratch = sm + n * n + (n + 1) * (n + 1) + 64;
+  if (map.u == n) block_sum_parts(parts, nparts, n * n, slices, scratch, sm);
+  else            block_sum_parts(parts, nparts, map.u * map.u, slices, scratch, sm + n * n);
+  brute_from_table(map, n, f, total, sel, status, sm);
+}
 
 // Interleaved part classes for block_sum_parts: as many as fit `budget` bytes of scratch, at most 8,
 // dividing `threads`.

@@ -138,22 +138,37 @@ k6_study(const __grid_constant__ RowTable rows, const int n, const Geom g, const
   __syncthreads();
   if (!last) return;
   __threadfence();
-  if (threadIdx.x <= n) {
-    // entry 0: sum avg^2 -> stats[0]; entry 1 + i: deviations of row i -> stats[2 + i]
-    const double* col = parts + threadIdx.x;
-    double s = 0.;
-    int p = 0;
-    for (; p + 8 <= (int)gridDim.x; p += 8) {
-      double t[8];
+  // Final sum of the gridDim.x blocks by the last CTA.  One thread per entry walking all blocks was a
+  // chain of ~gridDim.x / 8 dependent L2 round trips (~20 us at 296 blocks: half of the kernel at
+  // d = 1.3M); instead the blocks are split in S interleaved classes, thread (class s, entry c) adds
+  // its class in ascending order with all loads in flight, and the S class sums are added in class
+  // order: a fixed order for a given grid, every load independent.
+  {
+    const int width = n + 1;                        // entry 0: sum avg^2; entry 1 + i: deviations of row i
+    const int S = kStThreads / width;               // >= 3 (n <= 64)
+    const int c = threadIdx.x % width, cls = threadIdx.x / width;
+    double* partial = &warp_tot[0][0];              // S * width <= 256 doubles of the (now free) warp table
+    if (cls < S) {
+      double sum = 0.;
+      int p = cls;
+      for (; p + 7 * S < (int)gridDim.x; p += 8 * S) {
+        double t[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) t[u] = __ldcg(col + (size_t)(p + u) * (n + 1));
+        for (int u = 0; u < 8; ++u) t[u] = __ldcg(parts + (size_t)(p + u * S) * width + c);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) s += t[u];
+        for (int u = 0; u < 8; ++u) sum += t[u];
+      }
+      for (; p < (int)gridDim.x; p += S) sum += __ldcg(parts + (size_t)p * width + c);
+      partial[cls * width + c] = sum;
     }
-    for (; p < (int)gridDim.x; ++p) s += __ldcg(col + (size_t)p * (n + 1));
-    stats[threadIdx.x == 0 ? 0 : 1 + threadIdx.x] = s;
-  } else if (threadIdx.x == kMaxN + 1) {
-    stats[1] = (double)__uint_as_float(atomicMax(absmax_bits, 0u));
+    __syncthreads();
+    if (threadIdx.x < width) {
+      double sum = 0.;
+      for (int k = 0; k < S; ++k) sum += partial[k * width + threadIdx.x];
+      stats[threadIdx.x == 0 ? 0 : 1 + threadIdx.x] = sum;
+    } else if (threadIdx.x == kMaxN + 1) {
+      stats[1] = (double)__uint_as_float(atomicMax(absmax_bits, 0u));
+    }
   }
 }
 

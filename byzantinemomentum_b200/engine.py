@@ -23,13 +23,21 @@ from . import _lib, hostmem
 __all__ = ["average", "median", "trmean", "phocas", "meamed", "krum", "bulyan", "brute", "aksel", "cge",
            "pairdist_partial", "rowdist_partial", "krum_select", "bulyan_select", "brute_select",
            "rowdist_select", "average_selected", "bulyan_reduce", "avg_dev_max_async", "compute_avg_dev_max",
-           "config", "Plan"]
+           "config", "Plan", "pair_cache_stats", "GradientStack"]
 
 class _Config:
   """ strict_status: after brute / bulyan, read the device status word (one 4-byte D2H copy,
   i.e. a stream sync) and raise where the reference raises (brute.py:67, bulyan.py:70).
-  When False the call stays asynchronous and a failed rule yields an all-NaN vector. """
+  When False the call stays asynchronous and a failed rule yields an all-NaN vector.
+  reuse_distances: Multi-Krum / Bulyan / brute on CUDA tensors keep the table of squared pairwise
+  distances of their last call; a following call whose rows are, but for 1..4 of them, the very
+  same unmodified tensor objects (identity, address and in-place version all equal) only
+  computes the distances of the new rows — the attacks' line search, attacks/identical.py:68-77,
+  evaluates the rule up to 16 times per step on the same honest gradients.  Results are
+  bit-identical either way.  A caller that rewrites a gradient behind PyTorch's back (`.data`,
+  raw pointers, external kernels: no version bump) must switch this off. """
   strict_status = True
+  reuse_distances = True
 config = _Config()
 
 # ---------------------------------------------------------------------------- #
@@ -232,6 +240,81 @@ def meamed(gradients, f):
   return _coordinate("meamed", gradients, f)
 
 # ---------------------------------------------------------------------------- #
+# Distance reuse across calls
+
+class _PairCache:
+  """ Per device: the unique rows of the last Multi-Krum / Bulyan / brute call (weak references,
+  addresses, versions, their positions in the table) and two device buffers holding the table of
+  squared distances (the library reads one, writes the other). """
+  def __init__(self, device):
+    self.buffers = [torch.empty(_lib.MAX_N * _lib.MAX_N, dtype=torch.float64, device=device) for _ in range(2)]
+    self.current = 0          # buffer holding the last table
+    self.rows = {}            # id(tensor) -> (weakref, data_ptr, version, index)
+    self.u = 0
+    self.d = -1
+    self.stream = None
+    self.mode = ctypes.c_int(-1)
+    self.stats = dict(full=0, star=0, off=0)
+  def old_index(self, gradients, d, stream):
+    """ (ctypes int32[n] or None, cache_in ptr or None, u_old) for this call. """
+    if self.u == 0 or self.d != d or self.stream != stream or not self.rows:
+      return None, None, 0
+    n = len(gradients)
+    table = (ctypes.c_int32 * n)()
+    hits = 0
+    rows = self.rows
+    for i, g in enumerate(gradients):
+      entry = rows.get(id(g))
+      if entry is not None and entry[0]() is g and entry[1] == g.data_ptr() and entry[2] == g._version:
+        table[i] = entry[3]
+        hits += 1
+      else:
+        table[i] = -1
+    if hits == 0:
+      return None, None, 0
+    return table, self.buffers[self.current].data_ptr(), self.u
+  def update(self, gradients, d, stream):
+    """ After a call that wrote its table: remember its unique rows (pointer equality, first
+    appearance: the library's order). """
+    mode = self.mode.value
+    if mode < 0:
+      self.rows, self.u = {}, 0
+      self.stats["off"] += 1
+      return
+    self.stats["star" if mode == 1 else "full"] += 1
+    index, rows = {}, {}
+    try:
+      for g in gradients:
+        ptr = g.data_ptr()
+        k = index.setdefault(ptr, len(index))
+        if id(g) not in rows:
+          rows[id(g)] = (weakref.ref(g), ptr, g._version, k)
+    except TypeError:
+      rows, index = {}, {}
+    self.rows, self.u, self.d, self.stream = rows, len(index), d, stream
+    self.current ^= 1
+  def out_buffer(self):
+    return self.buffers[self.current ^ 1].data_ptr()
+
+_pair_caches = {}
+
+def _pair_cache(prep, gradients):
+  """ The cache to use for this call, or None (reuse switched off, staged host rows, packed copies). """
+  if not config.reuse_distances or prep.to_cpu or prep.rows is not None and prep.rows is not gradients:
+    return None
+  cache = _pair_caches.get(prep.device.index)
+  if cache is None:
+    cache = _pair_caches[prep.device.index] = _PairCache(prep.device)
+  return cache
+
+def pair_cache_stats(device_index=None):
+  """ Calls served per mode ({"full", "star", "off"}) by the distance cache of a device (tests, bench). """
+  if device_index is None:
+    device_index = torch.cuda.current_device()
+  cache = _pair_caches.get(device_index)
+  return dict(cache.stats) if cache is not None else dict(full=0, star=0, off=0)
+
+# ---------------------------------------------------------------------------- #
 # Distance-based rules (single device).  Each returns (out, selection) where `selection` is a
 # DEVICE int32 tensor (all n indices by increasing score/distance; brute: the n-f subset).
 
@@ -244,10 +327,18 @@ def krum(gradients, f, m):
   prep = _prepare(gradients)
   out = torch.empty(prep.d, dtype=torch.float32, device=prep.device)
   ws, meta = _aux(prep)
+  cache = _pair_cache(prep, gradients)
   with _on(prep.device):
-    code = _lib.lib().bz_krum(prep.ptrs, prep.n, int(f), int(m), prep.d, out.data_ptr(), meta.data_ptr(),
-                              ws.data_ptr(), ws.numel(), prep.stream)
+    if cache is None:
+      code = _lib.lib().bz_krum(prep.ptrs, prep.n, int(f), int(m), prep.d, out.data_ptr(), meta.data_ptr(),
+                                ws.data_ptr(), ws.numel(), prep.stream)
+    else:
+      old, cache_in, u_old = cache.old_index(gradients, prep.d, prep.stream)
+      code = _lib.lib().bz_krum_reuse(prep.ptrs, prep.n, int(f), int(m), prep.d, out.data_ptr(), meta.data_ptr(), old, cache_in, u_old,
+                                      cache.out_buffer(), ctypes.byref(cache.mode), ws.data_ptr(), ws.numel(), prep.stream)
   _lib.check(code, "bz_krum")
+  if cache is not None:
+    cache.update(gradients, prep.d, prep.stream)
   return _finish(prep, out), meta[:prep.n]
 
 def bulyan(gradients, f, m):
@@ -255,10 +346,18 @@ def bulyan(gradients, f, m):
   out = torch.empty(prep.d, dtype=torch.float32, device=prep.device)
   ws, meta = _aux(prep)
   status = meta[prep.n:]
+  cache = _pair_cache(prep, gradients)
   with _on(prep.device):
-    code = _lib.lib().bz_bulyan(prep.ptrs, prep.n, int(f), int(m), prep.d, out.data_ptr(), meta.data_ptr(),
-                                status.data_ptr(), ws.data_ptr(), ws.numel(), prep.stream)
+    if cache is None:
+      code = _lib.lib().bz_bulyan(prep.ptrs, prep.n, int(f), int(m), prep.d, out.data_ptr(), meta.data_ptr(),
+                                  status.data_ptr(), ws.data_ptr(), ws.numel(), prep.stream)
+    else:
+      old, cache_in, u_old = cache.old_index(gradients, prep.d, prep.stream)
+      code = _lib.lib().bz_bulyan_reuse(prep.ptrs, prep.n, int(f), int(m), prep.d, out.data_ptr(), meta.data_ptr(), status.data_ptr(),
+                                        old, cache_in, u_old, cache.out_buffer(), ctypes.byref(cache.mode), ws.data_ptr(), ws.numel(), prep.stream)
   _lib.check(code, "bz_bulyan")
+  if cache is not None:
+    cache.update(gradients, prep.d, prep.stream)
   if config.strict_status:
     _raise_status(int(status.item()))
   return _finish(prep, out), meta[:prep.n]
@@ -268,10 +367,18 @@ def brute(gradients, f):
   out = torch.empty(prep.d, dtype=torch.float32, device=prep.device)
   ws, meta = _aux(prep)
   status = meta[prep.n:]
+  cache = _pair_cache(prep, gradients)
   with _on(prep.device):
-    code = _lib.lib().bz_brute(prep.ptrs, prep.n, int(f), prep.d, out.data_ptr(), meta.data_ptr(),
-                               status.data_ptr(), ws.data_ptr(), ws.numel(), prep.stream)
+    if cache is None:
+      code = _lib.lib().bz_brute(prep.ptrs, prep.n, int(f), prep.d, out.data_ptr(), meta.data_ptr(),
+                                 status.data_ptr(), ws.data_ptr(), ws.numel(), prep.stream)
+    else:
+      old, cache_in, u_old = cache.old_index(gradients, prep.d, prep.stream)
+      code = _lib.lib().bz_brute_reuse(prep.ptrs, prep.n, int(f), prep.d, out.data_ptr(), meta.data_ptr(), status.data_ptr(),
+                                       old, cache_in, u_old, cache.out_buffer(), ctypes.byref(cache.mode), ws.data_ptr(), ws.numel(), prep.stream)
   _lib.check(code, "bz_brute")
+  if cache is not None:
+    cache.update(gradients, prep.d, prep.stream)
   if config.strict_status:
     _raise_status(int(status.item()))
   return _finish(prep, out), meta[:prep.n - int(f)]
@@ -314,6 +421,35 @@ def avg_dev_max_async(samples):
   _lib.check(code, "bz_avg_dev_max")
   return avg, stats
 
+class _StudyMemo:
+  """ Last `compute_avg_dev_max` result, valid for the very same tensor objects at the same
+  addresses and in-place versions (weak references: a dead or different tensor never matches).
+  attack.py:846-847 asks for the sampled and for the honest gradients; without worker/server-side
+  momentum and with nb_for_study = nb_honests those are the SAME tensors (`grad_honests =
+  grad_sampleds[:nb_honests]`, attack.py:808): the second pass over n x d is saved. """
+  def __init__(self):
+    self.refs = self.state = self.result = None
+  def lookup(self, samples):
+    if self.refs is None or len(self.refs) != len(samples):
+      return None
+    for ref, g in zip(self.refs, samples):
+      if ref() is not g:
+        return None
+    if tuple((g.data_ptr(), g._version) for g in samples) != self.state:
+      return None
+    avg, a, b, c = self.result
+    return avg.clone(), a, b, c                               # callers own the average they get (grad_pasts keeps it)
+  def store(self, samples, result):
+    try:
+      self.refs = tuple(weakref.ref(g) for g in samples)
+    except TypeError:
+      self.refs = None
+      return
+    self.state = tuple((g.data_ptr(), g._version) for g in samples)
+    self.result = result
+
+_study_memo = _StudyMemo()
+
 def compute_avg_dev_max(samples):
   """ Drop-in for `tools.compute_avg_dev_max(samples)` (tools/pytorch.py:97-125): returns
   (average gradient or None, norm of the average, norm standard deviation, max |coordinate| of the
@@ -321,6 +457,14 @@ def compute_avg_dev_max(samples):
   n = len(samples)
   if n == 0:
     return None, math.nan, math.nan, math.nan                 # :105-106
+  hit = _study_memo.lookup(samples)
+  if hit is not None:
+    return hit
+  result = _compute_avg_dev_max(samples, n)
+  _study_memo.store(samples, (result[0].clone(),) + result[1:])
+  return result
+
+def _compute_avg_dev_max(samples, n):
   avg, stats = avg_dev_max_async(samples)
   host = stats.tolist()                                       # the only synchronisation
   norm_avg = ctypes.c_float(math.sqrt(host[0])).value      # :110 returns an fp32 norm: same rounding in the logs
@@ -481,6 +625,73 @@ def bulyan_reduce(gradients, f, m, order, status=None):
     code = _lib.lib().bz_bulyan_reduce(prep.ptrs, prep.n, int(f), int(m), order.data_ptr(), st_ptr, prep.d, out.data_ptr(), prep.stream)
   _lib.check(code, "bz_bulyan_reduce")
   return out
+
+# ---------------------------------------------------------------------------- #
+# Gradient production (attack.py:776-780, 791-795, 799-810)
+
+class GradientStack:
+  """ The n worker gradients of a step as rows of ONE preallocated [n, d] device buffer, filled by
+  `bz_gradient_row`: per worker, one pass that clips (norm and scale stay on the device: no
+  `.item()`), writes the sampled row (the reference's `grad.clone()`) and applies the momentum
+  placement — instead of norm + mul_ + clone + mul_ + add_ (7 vector passes and a host sync).
+
+      stack = GradientStack(n_sampled, d, device)            # once
+      for i in range(n_sampled):                             # every step
+        grad, loss = model.backprop(outloss=True)
+        stack.push(i, grad, clip=args.gradient_clip)                              # momentum at "update"
+        stack.push(i, grad, clip, worker_momentum=gmtm[i], mu=0.9, dampening=0.)   # at "worker": gmtm[i] updated in place
+        stack.push(i, grad, clip, server_momentum=gserver, mu=0.9, dampening=0.)   # at "server": honest row i written
+      rows = stack.sampled(k)  /  stack.honest(k)             # lists of row views for the rule
+
+  Bit-exact with the ATen sequence (tests/test_cuda_gradient_rows.py); when clipping occurs the
+  scale factor may differ by 1 ulp (ATen's fp32 norm order is build specific). """
+  def __init__(self, n, d, device):
+    self.n, self.d, self.device = n, d, torch.device(device)
+    pitch = (d + 63) // 64 * 64                     # rows 256-byte aligned: vector loads, TMA bulk copies
+    self._sampled = torch.empty((n, pitch), dtype=torch.float32, device=self.device)
+    self._honest = None
+    self._pitch = pitch
+    self._lib = _lib.lib()
+  def _honest_buffer(self):
+    if self._honest is None:
+      self._honest = torch.empty((self.n, self._pitch), dtype=torch.float32, device=self.device)
+    return self._honest
+  def push(self, i, grad, clip=None, worker_momentum=None, server_momentum=None, mu=0., dampening=0.):
+    """ Row i <- this worker's gradient.  Returns the sampled row (a view of the buffer). """
+    if grad.dtype != torch.float32 or grad.dim() != 1 or grad.numel() != self.d or not grad.is_contiguous() or grad.device != self.device:
+      raise ValueError("grad must be a contiguous float32 vector of d elements on the stack's device")
+    if worker_momentum is not None and server_momentum is not None:
+      raise ValueError("worker-side and server-side momentum are exclusive (attack.py:799-810)")
+    row = self._sampled[i, :self.d]
+    mode, mom, honest = 0, None, None
+    if worker_momentum is not None:
+      mode, mom = 1, worker_momentum
+    elif server_momentum is not None:
+      mode, mom, honest = 2, server_momentum, self._honest_buffer()[i, :self.d]
+    if mom is not None and (mom.dtype != torch.float32 or mom.shape != (self.d,) or not mom.is_contiguous() or mom.device != self.device):
+      raise ValueError("momentum must be a contiguous float32 vector like the gradient")
+    stream = torch.cuda.current_stream(self.device).cuda_stream
+    ws = _workspace(self.device, stream)
+    with _on(self.device):
+      code = self._lib.bz_gradient_row(grad.data_ptr(), self.d, float(clip) if clip is not None else 0., row.data_ptr(), mode,
+                                       None if mom is None else mom.data_ptr(), float(mu), 1. - float(dampening),
+                                       None if honest is None else honest.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+    _lib.check(code, "bz_gradient_row")
+    # the kernel wrote through raw pointers: tell PyTorch (the identity/version keyed caches of this
+    # package — prepared arguments, selection, distance table, study memo — rely on the counter;
+    # views share it with their base, so every row of the buffer is invalidated: conservative)
+    _bump = torch.autograd.graph.increment_version
+    _bump(row)
+    if mode == 1:
+      _bump(mom)
+    elif mode == 2:
+      _bump(honest)
+    return row
+  def sampled(self, count=None):
+    return [self._sampled[i, :self.d] for i in range(self.n if count is None else count)]
+  def honest(self, count=None):
+    buf = self._honest_buffer()
+    return [buf[i, :self.d] for i in range(self.n if count is None else count)]
 
 # ---------------------------------------------------------------------------- #
 # Prepared calls

@@ -29,7 +29,7 @@ import torch.distributed as dist
 
 from . import engine as _engine
 
-__all__ = ["aggregate", "aggregate_p2p", "compute_avg_dev_max", "replicate", "PeerExchange", "ShardedPlan", "COORDINATE_WISE", "DISTANCE_BASED"]
+__all__ = ["aggregate", "aggregate_p2p", "compute_avg_dev_max", "replicate", "apply_update", "shard_bounds", "PeerExchange", "ShardedPlan", "COORDINATE_WISE", "DISTANCE_BASED"]
 
 COORDINATE_WISE = ("average", "median", "trmean", "phocas", "meamed")
 DISTANCE_BASED = ("krum", "bulyan", "brute", "aksel", "cge")
@@ -382,3 +382,52 @@ def replicate(shard, group=None):
   if all(l == longest for l in lengths):
     return gathered
   return torch.cat([gathered[r * longest:r * longest + lengths[r]] for r in range(world)])
+
+
+def shard_bounds(d, world, rank):
+  """ [lo, hi) of rank's columns under the even split used throughout (the last shards may be shorter). """
+  per = (d + world - 1) // world
+  lo = min(d, rank * per)
+  return lo, min(d, lo + per)
+
+def apply_update(params, shard, lr, weight_decay=0., group=None):
+  """ Close the d-sharded loop: the model update of `experiments/model.py:368-380`
+  — `set_gradient(aggregated)` + `optimizer.step()` of the reference's plain SGD (attack.py:544:
+  momentum 0, dampening 0, weight decay w) — done by every rank ON ITS SHARD of the flat parameter
+  vector, followed by ONE all-gather of the updated parameters.  Against `replicate(shard)` + a
+  replicated update this moves the same d*4 bytes over NVLink but does the update arithmetic once
+  instead of R times and never materialises the full aggregated gradient.
+  The arithmetic is torch's SGD: g' = g + w p (only when w != 0), p <- p - lr g', in place, fp32.
+  Args:
+    params        Flat fp32 parameter vector [d], replicated on every rank (updated in place)
+    shard         This rank's [hi - lo] slice of the aggregated gradient (`ShardedPlan.out`)
+    lr            Learning rate
+    weight_decay  L2 coefficient w
+    group         Process group (default: the world)
+  Returns:
+    `params`
+  """
+  world = dist.get_world_size(group) if dist.is_initialized() else 1
+  rank = dist.get_rank(group) if dist.is_initialized() else 0
+  d = params.numel()
+  lo, hi = shard_bounds(d, world, rank)
+  if shard.numel() != hi - lo:
+    raise ValueError(f"shard of {shard.numel()} elements, expected {hi - lo} (columns {lo}..{hi} of {d})")
+  mine = params[lo:hi]
+  if weight_decay != 0.:
+    mine.add_(shard.add(mine, alpha=weight_decay), alpha=-lr)
+  else:
+    mine.add_(shard, alpha=-lr)
+  if world == 1:
+    return params
+  per = (d + world - 1) // world
+  if per * world == d:
+    # in place with NCCL (rank r's slot of the output IS its shard); other backends get a copy
+    dist.all_gather_into_tensor(params, mine if dist.get_backend(group) == "nccl" else mine.clone(), group=group)
+    return params
+  # ragged split: pad the shards to `per` for the collective, trim after it
+  padded = mine if mine.numel() == per else torch.cat([mine, mine.new_zeros(per - mine.numel())])
+  gathered = torch.empty(world * per, dtype=params.dtype, device=params.device)
+  dist.all_gather_into_tensor(gathered, padded.contiguous(), group=group)
+  params.copy_(gathered[:d])
+  return params

@@ -46,6 +46,7 @@ extern "C" {
 
 #define BZ_MAX_N 64
 #define BZ_MAX_PEERS 16   /* ranks whose partial blocks one selection kernel can read in place */
+#define BZ_CACHE_DOUBLES (BZ_MAX_N * BZ_MAX_N)   /* doubles in a distance-table buffer of the bz_*_reuse calls */
 
 #define BZ_OK            0
 #define BZ_EINVAL       -1   /* bad argument (null pointer, n/f/m out of executable range) */
@@ -99,6 +100,30 @@ BZ_API int bz_aksel(const float* const* rows, int n, int f, int mode, int64_t d,
 /* aggregators/cge.py:28-57 — average of the n-f smallest-norm rows (clone + add_ + div_). */
 BZ_API int bz_cge(const float* const* rows, int n, int f, int64_t d, float* out,
            int32_t* order, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- Multi-Krum / Bulyan / brute with distance reuse ----------------------
+ * attacks/identical.py:68-77 (the attacks' line search) calls the rule up to 16 times per step with
+ * the SAME honest tensors and one new Byzantine tensor per evaluation: every honest-honest distance
+ * is invariant.  These variants take the table of squared distances a previous call left behind:
+ *   old_index  HOST int32[n]: position of rows[i] in that table — the caller vouches that the
+ *              row's content is unchanged since — or -1 for a row that was not in it; NULL = no reuse
+ *   cache_in   that table, DEVICE double[u_old * u_old] (NULL = none)
+ *   cache_out  DEVICE double[BZ_CACHE_DOUBLES], different from cache_in: receives this call's
+ *              u x u table over the unique rows (pointer equality, first-appearance order)
+ *   mode_out   HOST int: 1 = only the pairs of the new rows were computed (1..4 new unique rows
+ *              and the launch geometry of the cached call), 0 = full pass, table written,
+ *              -1 = full pass and NO table written (unaligned rows: the round-1 kernel ran)
+ * Results are bit-identical to the plain calls: a reused pair has exactly the bits the full pass
+ * gives it (same coordinate-to-lane mapping, same summation order). */
+BZ_API int bz_krum_reuse(const float* const* rows, int n, int f, int m, int64_t d, float* out, int32_t* order,
+                         const int32_t* old_index, const double* cache_in, int u_old, double* cache_out,
+                         int* mode_out, void* ws, size_t ws_bytes, void* stream);
+BZ_API int bz_bulyan_reuse(const float* const* rows, int n, int f, int m, int64_t d, float* out, int32_t* order,
+                           int32_t* status, const int32_t* old_index, const double* cache_in, int u_old,
+                           double* cache_out, int* mode_out, void* ws, size_t ws_bytes, void* stream);
+BZ_API int bz_brute_reuse(const float* const* rows, int n, int f, int64_t d, float* out, int32_t* sel,
+                          int32_t* status, const int32_t* old_index, const double* cache_in, int u_old,
+                          double* cache_out, int* mode_out, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- Phases for the d-sharded multi-GPU path ------------------------
  * Each rank runs phase A on its shard, the R partial blocks are all-gathered (one small
@@ -156,6 +181,22 @@ BZ_API int bz_bulyan_reduce(const float* const* rows, int n, int f, int m, const
  * norm_dev = sqrt(sum_i stats[2+i] / (n-1)). */
 BZ_API int bz_avg_dev_max(const float* const* rows, int n, int64_t d, float* avg, double* stats,
                           void* ws, size_t ws_bytes, void* stream);
+
+/* ---- Gradient production: attack.py:776-780 / 791-795 (clip + clone per
+ * worker) and :799-810 (momentum placement) for ONE worker gradient, in one pass.
+ *   grad      device fp32[d], the model's flat gradient (read only)
+ *   clip      > 0: `if norm > clip: g *= clip / norm` (the norm and the scale stay on the device,
+ *             no host sync); <= 0: no clipping
+ *   sampled   device fp32[d] or NULL: receives the (clipped) gradient — `grad.clone()`, a row of
+ *             the caller's preallocated [n, d] buffer
+ *   mode 0    nothing else
+ *   mode 1    worker-side momentum: momentum[d] <- momentum * mu + alpha * g'   (in place; the
+ *             momentum vector IS the honest gradient the rule reads, attack.py:802-803)
+ *   mode 2    server-side momentum: honest[d] <- g' * alpha + mu * momentum     (attack.py:807)
+ *   alpha = 1 - dampening.  Bit-exact with the ATen operator sequence (the clip scale to 1 ulp).
+ *   ws        needed only with clip > 0 (bz_workspace_bytes(1) suffices). */
+BZ_API int bz_gradient_row(const float* grad, int64_t d, double clip, float* sampled, int mode, float* momentum,
+                           double mu, double alpha, float* honest, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

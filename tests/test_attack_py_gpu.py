@@ -54,6 +54,14 @@ OTHER = {
   "c3-krum": ("b200-krum", "krum", 25, 5, dict(attack_args=["factor:1.1"], model="empire-cnn", dataset="cifar10", momentum_at="worker")),
   "c3-bulyan": ("b200-bulyan", "bulyan", 25, 5, dict(attack_args=["factor:1.1"], model="empire-cnn", dataset="cifar10", momentum_at="worker")),
 }
+# gradient production fused into GradientStack.push (tools/drive_attack.py --fuse-gradients: attack.py's
+# clip / clone / momentum statements swapped IN MEMORY): tag -> (rule, n, f, momentum placement, clip)
+FUSED = {
+  "fuse-update": ("b200-krum", 11, 3, "update", "2"),
+  "fuse-worker": ("b200-krum", 11, 3, "worker", "2"),
+  "fuse-server": ("b200-trmean", 11, 3, "server", "0.5"),
+  "fuse-noclip": ("b200-median", 11, 3, "worker", None),
+}
 INFLUENCE = ("krum", "brute", "aksel", "cge", "average")
 
 @pytest.fixture(scope="module")
@@ -66,6 +74,10 @@ def runs(tmp_path_factory):
   for tag, (ours, stock, n, f, kw) in OTHER.items():
     jobs.append(dict(tag=tag, install_tools=True, args=_args(tmp / tag, ours, n, f, **kw)))
     jobs.append(dict(tag=tag + "/stock", install_tools=False, args=_args(tmp / (tag + "-stock"), stock, n, f, **kw)))
+  for tag, (gar, n, f, where, clip) in FUSED.items():
+    extra = [] if clip is None else ["--gradient-clip", clip]
+    jobs.append(dict(tag=tag, install_tools=True, fuse_gradients=True, args=_args(tmp / tag, gar, n, f, ["factor:1.1"], momentum_at=where)[:-2] + extra + ["--result-directory", str(tmp / tag)]))
+    jobs.append(dict(tag=tag + "/stock", install_tools=True, fuse_gradients=False, args=_args(tmp / (tag + "-stock"), gar, n, f, ["factor:1.1"], momentum_at=where)[:-2] + extra + ["--result-directory", str(tmp / (tag + "-stock"))]))
   batch = tmp / "batch.json"
   batch.write_text(json.dumps(jobs))
   cmd = [sys.executable, str(ROOT / "tools" / "drive_attack.py"), "--count-calls", "--install-tools", "--batch", str(batch)]
@@ -73,12 +85,14 @@ def runs(tmp_path_factory):
   assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
   result = {}
   for job in jobs:
-    result[job["tag"]] = dict(ok=False, calls={}, rows=None, dir=pathlib.Path(job["args"][-1]))
+    result[job["tag"]] = dict(ok=False, calls={}, rows=None, dir=pathlib.Path(job["args"][-1]), pushes=0)
   for line in proc.stdout.splitlines():
     if line.startswith("run-ok "):
       result[line.split()[1]]["ok"] = True
     elif line.startswith("run-failed "):
       result[line.split()[1]]["error"] = line
+    elif line.startswith("fused-pushes "):
+      result[line.split()[1]]["pushes"] = int(line.split()[2])
     elif line.startswith("gar-calls "):
       _, tag, name, calls, infl = line.split()
       result[tag]["calls"][name] = (int(calls), int(infl))
@@ -130,3 +144,15 @@ def test_attack_py_device_hops_momentum_and_cifar_shape(runs, tag):
   assert theirs["ok"], theirs.get("error")
   assert mine["calls"][ours][0] == STEPS
   _same_study(mine["rows"], theirs["rows"], stock in INFLUENCE, rel=5e-4)
+
+@pytest.mark.parametrize("tag", sorted(FUSED))
+def test_attack_py_with_fused_gradient_production(runs, tag):
+  """ attack.py:775-780 / 790-795 (clip + clone) and :799-808 (momentum placement)
+  executed as `GradientStack.push` — one kernel per worker writing rows of one [n, d] buffer — inside
+  the otherwise unmodified attack.py; the run must log what the unfused run logs. """
+  gar, n, f, where, clip = FUSED[tag]
+  mine, theirs = runs[tag], runs[tag + "/stock"]
+  assert mine["ok"], mine.get("error", runs["__stdout__"][-3000:])
+  assert theirs["ok"], theirs.get("error")
+  assert mine["pushes"] == STEPS * (n - f) and theirs["pushes"] == 0        # nb_for_study = nb_honests = n - f gradients per step
+  _same_study(mine["rows"], theirs["rows"], gar[5:] in INFLUENCE, rel=5e-4)

@@ -55,6 +55,17 @@ def _worker(rank, world, port, queue):
       poisoned = shard
     study["nan"] = sharded.compute_avg_dev_max(poisoned, backend=OracleBackend())[1:]
     out["study"] = study
+    # model update on the shard + all-gather of the parameters (ragged and even splits)
+    upd = {}
+    for dd in (d, d - 1):
+      params = torch.linspace(-1., 1., dd)
+      grad = torch.sin(torch.arange(dd, dtype=torch.float32))
+      l, h = sharded.shard_bounds(dd, world, rank)
+      for wd in (0., 0.01):
+        mine = params.clone()
+        sharded.apply_update(mine, grad[l:h].clone(), 0.05, weight_decay=wd)
+        upd[(dd, wd)] = mine.numpy().copy()
+    out["update"] = upd
     out["replicated"] = sharded.replicate(sharded.aggregate("trmean", shard, f=3, backend=OracleBackend())).numpy().copy()
     queue.put((rank, lo, hi, out))
   finally:
@@ -107,6 +118,14 @@ def test_two_rank_sharding_matches_single_process():
   for r in (0, 1):
     norm_avg, norm_dev, norm_max = got[r][3]["study"]["nan"]
     assert math.isnan(norm_avg) and math.isnan(norm_dev) and math.isnan(norm_max)
+  # sharded model update: every rank ends with the parameters a replicated torch SGD step gives
+  for dd in (601, 600):
+    for wd in (0., 0.01):
+      params = torch.nn.Parameter(torch.linspace(-1., 1., dd))
+      params.grad = torch.sin(torch.arange(dd, dtype=torch.float32))
+      torch.optim.SGD([params], lr=0.05, momentum=0., dampening=0., weight_decay=wd).step()
+      for r in range(2):
+        parity.assert_bit_exact(got[r][3]["update"][(dd, wd)], params.detach().numpy(), f"sharded SGD step d={dd} wd={wd} on rank {r}")
   # replicated output: every rank ends with the full vector (shards of 301 and 300 columns)
   for r in (0, 1):
     parity.assert_bit_exact(got[r][3]["replicated"], orc.trmean(rows, 3), f"replicated output on rank {r}")

@@ -1,8 +1,11 @@
 set -x
 mkdir -p gpurun_out
-( timeout 1200 python -m pytest tests -q -m gpu -x 2>&1 | tail -8 ) > gpurun_out/r2_t4.log 2>&1
-( timeout 300 python tools/abk2.py 2>&1 | tail -12 ) > gpurun_out/r2_rules_fused2.log 2>&1
-( BYZAGG_K2_BIGTILE=1 timeout 300 python tools/k2_ab.py --cases 40:1310922,51:1310922,51:4568373 --no-alias --only ring 2>&1 | tail -12 ) > gpurun_out/r2_bigtile.log 2>&1
-( timeout 300 python tools/k2_ab.py --cases 25:1310922,40:1310922,51:1310922,51:4568373 --no-alias --only ring 2>&1 | tail -12 ) > gpurun_out/r2_smalltile.log 2>&1
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r2_rules_launches2.csv python tools/prof_rules.py 25 5 1310922 krum,bulyan > gpurun_out/ncu3.log 2>&1
-tail -4 gpurun_out/r2_t4.log; cat gpurun_out/r2_rules_fused2.log gpurun_out/r2_bigtile.log gpurun_out/r2_smalltile.log
+( timeout 900 python -m pytest tests/test_cuda_reuse.py tests/test_cuda_gradient_rows.py tests/test_attack_py_gpu.py -q -m gpu 2>&1 | tail -30 ) > gpurun_out/r2_t9.log 2>&1
+( timeout 300 python tools/linesearch_time.py gpurun_out/r2_linesearch.json 2>&1 | tail -8 ) > gpurun_out/r2_linesearch.log 2>&1
+( timeout 900 python bench.py --steps 200 --warmup 10 2> gpurun_out/r2_bench1.err | tail -1 ) > gpurun_out/r2_bench1.json
+tail -30 gpurun_out/r2_t9.log; cat gpurun_out/r2_linesearch.log; tail -3 gpurun_out/r2_bench1.err; python - <<'PY'
+import json
+l=json.loads(open('gpurun_out/r2_bench1.json').read())
+print({k:l[k] for k in ('value','ms_per_step','gpu_launches','clocks')}); print(l['roofline']); print(l['e2e']); print(l['cpu_baseline'])
+for r in l.get('sweep',[]): print(r)
+PY

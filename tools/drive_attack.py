@@ -23,6 +23,85 @@ import sys
 
 SHAPES = {"mnist": ((1, 28, 28), 10), "cifar10": ((3, 32, 32), 10), "cifar100": ((3, 32, 32), 100)}
 
+CLIP_AND_CLONE = """          # Gradient clip and append
+          if args.gradient_clip is not None:
+            grad_norm = grad.norm().item()
+            if grad_norm > args.gradient_clip:
+              grad.mul_(args.gradient_clip / grad_norm)
+          grad_sampleds.append(grad.clone().detach_())
+"""
+CLIP_AND_CLONE_NEW = """          # (byzantinemomentum_b200) clip + clone + momentum placement in one pass, into a row of the stack
+          grad_sampleds.append(__bz_rows.push(len(grad_sampleds), grad, args, globals()))
+"""
+MOMENTUM = """    if args.momentum_at == "worker":
+      grad_honests = list()
+      for gmtm, grad in zip(grad_momentum_workers, grad_sampleds[:args.nb_honests]):
+        gmtm.mul_(args.momentum).add_(grad, alpha=(1. - args.dampening))
+        grad_honests.append(gmtm)
+    elif args.momentum_at == "server":
+      grad_honests = list()
+      for grad in grad_sampleds[:args.nb_honests]:
+        grad_honests.append(grad.mul(1. - args.dampening).add_(grad_momentum_server, alpha=args.momentum))
+"""
+MOMENTUM_NEW = """    if args.momentum_at == "worker":
+      grad_honests = __bz_rows.honests_worker(grad_momentum_workers, grad_sampleds, args)
+    elif args.momentum_at == "server":
+      grad_honests = __bz_rows.honests_server(grad_momentum_server, grad_sampleds, args)
+"""
+
+class FusedRows:
+  """ What the rewritten statements call.  CUDA gradients go through `GradientStack.push` (one
+  kernel per worker); anything else runs the reference's own statements, unchanged. """
+  def __init__(self, bz, torch):
+    self.bz, self.torch, self.stack, self.fused = bz, torch, None, False
+    self.pushes = 0
+  def push(self, i, grad, args, g):
+    if not grad.is_cuda:
+      self.fused = False
+      if args.gradient_clip is not None:
+        grad_norm = grad.norm().item()
+        if grad_norm > args.gradient_clip:
+          grad.mul_(args.gradient_clip / grad_norm)
+      return grad.clone().detach_()
+    n = max(args.nb_honests, args.nb_for_study)
+    if self.stack is None or self.stack.n != n or self.stack.d != grad.numel() or self.stack.device != grad.device:
+      self.stack = self.bz.GradientStack(n, grad.numel(), grad.device)
+    self.fused = True
+    self.pushes += 1
+    kwargs = {}
+    if i < args.nb_honests:
+      if args.momentum_at == "worker":
+        kwargs = dict(worker_momentum=g["grad_momentum_workers"][i], mu=args.momentum, dampening=args.dampening)
+      elif args.momentum_at == "server":
+        kwargs = dict(server_momentum=g["grad_momentum_server"], mu=args.momentum, dampening=args.dampening)
+    return self.stack.push(i, grad.detach(), clip=args.gradient_clip, **kwargs)
+  def honests_worker(self, workers, sampleds, args):
+    if self.fused:
+      return list(workers[:args.nb_honests])                  # already updated by push
+    out = list()
+    for gmtm, grad in zip(workers, sampleds[:args.nb_honests]):
+      gmtm.mul_(args.momentum).add_(grad, alpha=(1. - args.dampening))
+      out.append(gmtm)
+    return out
+  def honests_server(self, server, sampleds, args):
+    if self.fused:
+      return self.stack.honest(args.nb_honests)
+    return [grad.mul(1. - args.dampening).add_(server, alpha=args.momentum) for grad in sampleds[:args.nb_honests]]
+
+def run_attack(path, fuse, helper):
+  """ `python3 attack.py` (sys.argv already set): plain runpy, or — with `fuse` — the same source
+  with the two statement groups above swapped in memory.  Each anchor must occur exactly as often
+  as in the reference (2 and 1), else nothing runs. """
+  if not fuse:
+    return runpy.run_path(str(path), run_name="__main__")
+  source = path.read_text()
+  if source.count(CLIP_AND_CLONE) != 2 or source.count(MOMENTUM) != 1:
+    raise SystemExit("drive_attack: attack.py does not contain the expected statements; refusing to rewrite")
+  source = source.replace(CLIP_AND_CLONE, CLIP_AND_CLONE_NEW).replace(MOMENTUM, MOMENTUM_NEW)
+  scope = {"__name__": "__main__", "__file__": str(path), "__builtins__": __builtins__, "__bz_rows": helper}
+  exec(compile(source, str(path), "exec"), scope)
+  return scope
+
 def main():
   parser = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
   parser.add_argument("--reference", default=None, help="root of the ByzantineMomentum checkout (default: $BYZ_REFERENCE, baseline/_ref, /root/reference)")
@@ -30,6 +109,8 @@ def main():
   parser.add_argument("--shape", default="mnist", choices=sorted(SHAPES), help="shape of the synthetic samples")
   parser.add_argument("--override", action="store_true", help="replace the stock rules instead of adding b200-<name>")
   parser.add_argument("--install-tools", action="store_true", help="also swap tools.compute_avg_dev_max for CUDA samples")
+  parser.add_argument("--fuse-gradients", action="store_true",
+    help="execute attack.py with its per-worker clip/clone/momentum statements (attack.py:775-780, 790-795, 799-808) replaced IN MEMORY by GradientStack.push (the file on disk is not touched; every anchor must match exactly)")
   parser.add_argument("--batch", default=None, help="JSON file with a list of {tag, args}: run attack.py once per entry in this process")
   parser.add_argument("rest", nargs=argparse.REMAINDER, help="arguments of attack.py (after --)")
   args = parser.parse_args()
@@ -96,18 +177,24 @@ def main():
       sys.argv = [str(ref / "attack.py")] + list(job["args"])
       tools.compute_avg_dev_max = cuda_study if job.get("install_tools", True) else stock_study
       try:
-        runpy.run_path(str(ref / "attack.py"), run_name="__main__")
+        helper = FusedRows(bz, torch)
+        run_attack(ref / "attack.py", bool(job.get("fuse_gradients", args.fuse_gradients)), helper)
         stream.write(f"run-ok {job['tag']}\n")
+        if helper.pushes:
+          stream.write(f"fused-pushes {job['tag']} {helper.pushes}\n")
       except BaseException as err:      # attack.py reports fatal errors through exit(1)
         stream.write(f"run-failed {job['tag']} {type(err).__name__}: {err}\n")
         traceback.print_exc(file=stream)
       report(job["tag"])
     return
   sys.argv = [str(ref / "attack.py")] + rest
+  helper = FusedRows(bz, torch)
   try:
-    runpy.run_path(str(ref / "attack.py"), run_name="__main__")
+    run_attack(ref / "attack.py", args.fuse_gradients, helper)
   finally:
     report("run")
+    if helper.pushes:
+      stream.write(f"fused-pushes run {helper.pushes}\n")
 
 if __name__ == "__main__":
   main()

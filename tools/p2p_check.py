@@ -36,8 +36,18 @@ def main():
       return e0.elapsed_time(e1) / K * 1e3
     t_nccl = timeit(lambda: sharded.aggregate(gar, rows, f=f))
     t_p2p = timeit(lambda: sharded.aggregate_p2p(gar, rows, f=f))
+    # the prepared calls: same shard, same selection, as the step-by-step ones
+    plan_n = sharded.ShardedPlan(gar, rows, f=f, exchange="nccl")
+    plan_p = sharded.ShardedPlan(gar, rows, f=f, exchange="p2p")
+    same_plan = torch.equal(plan_n(), a) and torch.equal(plan_p(), a) and torch.equal(plan_n.selection, sa[:plan_n.selection.numel()]) \
+                and torch.equal(plan_p.selection, sa[:plan_p.selection.numel()])
+    same_plan = same_plan and torch.equal(plan_p(), a) and torch.equal(plan_p(), a)       # both slots of the symmetric buffer
+    ok = ok and same_plan
+    t_plan_n, t_plan_p = timeit(plan_n, 200), timeit(plan_p, 200)
+    single = bz.Plan(gar, rows, f=f)
+    t_single = timeit(single, 200)
     if rank == 0:
-      print(f"{gar:7s} N={world}: identical={same}  nccl {t_nccl:7.1f} us/step   p2p {t_p2p:7.1f} us/step", flush=True)
+      print(f"{gar:7s} N={world}: identical={same} plans={same_plan}  aggregate: nccl {t_nccl:7.1f} p2p {t_p2p:7.1f} | ShardedPlan: nccl {t_plan_n:7.1f} p2p {t_plan_p:7.1f} | single-GPU Plan {t_single:7.1f} us/step", flush=True)
   flag = torch.tensor([1 if ok else 0], device=dev)
   dist.all_reduce(flag, op=dist.ReduceOp.MIN)
   if rank == 0:
