@@ -67,6 +67,15 @@ def _workspace(device, stream):
 
 _F32 = torch.float32
 
+_COPY_LANES = 4
+_copy_lanes = {}
+
+def _copy_streams(device):
+  lanes = _copy_lanes.get(device.index)
+  if lanes is None:
+    lanes = _copy_lanes[device.index] = [torch.cuda.Stream(device) for _ in range(_COPY_LANES)]
+  return lanes
+
 def _validate(gradients):
   """ One pass over the list: types, dtype, rank, length; returns (first, all_contiguous). """
   if not isinstance(gradients, (list, tuple)) or len(gradients) < 1:
@@ -151,11 +160,22 @@ def _prepare(gradients):
       pitch = (d + 63) // 64 * 64       # rows 256-byte aligned: keeps the vector-load path
       buf = torch.empty((len(uniq), pitch), dtype=torch.float32, device=device)
       _staging[key] = buf
+    # The row copies go out on several streams.  Measured (tools/h2d_probe2.py, two-socket host):
+    # pinned rows that live on the OTHER socket's memory copy at 8.5 GB/s on one stream and at
+    # 53 GB/s on two or more — with one stream the e2e step took 12.5 ms, 2.5x the box's own PCIe
+    # floor, and varied 4x between boxes depending on where the caller's pages happened to be.
+    current = torch.cuda.current_stream(device)
+    lanes = _copy_streams(device)
+    for lane in lanes:
+      lane.wait_stream(current)          # the previous call's kernels have finished with the staging buffer
     slot = {}
     for k, (ident, g) in enumerate(uniq.items()):
       row = buf[k, :d]
-      row.copy_(g, non_blocking=True)
+      with torch.cuda.stream(lanes[k % len(lanes)]):
+        row.copy_(g, non_blocking=True)
       slot[ident] = row
+    for lane in lanes:
+      current.wait_stream(lane)
     rows = [slot[id(g)] for g in gradients]
     keep = buf
     prep.to_cpu = True
@@ -256,16 +276,19 @@ class _PairCache:
     self.mode = ctypes.c_int(-1)
     self.stats = dict(full=0, star=0, off=0)
   def old_index(self, gradients, d, stream):
-    """ (ctypes int32[n] or None, cache_in ptr or None, u_old) for this call. """
-    if self.u == 0 or self.d != d or self.stream != stream or not self.rows:
+    """ (ctypes int32[n] or None, cache_in ptr or None, u_old) for this call.  One pass over the
+    rows; the addresses / versions read here are kept for `update`. """
+    self._ptrs = ptrs = [g.data_ptr() for g in gradients]
+    self._vers = vers = [g._version for g in gradients]
+    if self.u == 0 or self.d != d or self.stream != stream:
       return None, None, 0
     n = len(gradients)
     table = (ctypes.c_int32 * n)()
     hits = 0
-    rows = self.rows
+    get = self.rows.get
     for i, g in enumerate(gradients):
-      entry = rows.get(id(g))
-      if entry is not None and entry[0]() is g and entry[1] == g.data_ptr() and entry[2] == g._version:
+      entry = get(id(g))
+      if entry is not None and entry[1] == ptrs[i] and entry[2] == vers[i] and entry[0]() is g:
         table[i] = entry[3]
         hits += 1
       else:
@@ -283,12 +306,15 @@ class _PairCache:
       return
     self.stats["star" if mode == 1 else "full"] += 1
     index, rows = {}, {}
+    ref = weakref.ref
     try:
-      for g in gradients:
-        ptr = g.data_ptr()
-        k = index.setdefault(ptr, len(index))
-        if id(g) not in rows:
-          rows[id(g)] = (weakref.ref(g), ptr, g._version, k)
+      for g, ptr, ver in zip(gradients, self._ptrs, self._vers):
+        k = index.get(ptr)
+        if k is None:
+          k = index[ptr] = len(index)
+        key = id(g)
+        if key not in rows:
+          rows[key] = (ref(g), ptr, ver, k)
     except TypeError:
       rows, index = {}, {}
     self.rows, self.u, self.d, self.stream = rows, len(index), d, stream
@@ -754,6 +780,29 @@ class Plan:
       else:
         raise KeyError(f"unknown aggregation rule {gar!r}")
     self._fn, self._args, self._what = fn, args, "bz_" + gar
+    self._graph = None
+  def graph(self):
+    """ Capture the prepared call in a CUDA graph and return `replay`: a callable that launches the
+    whole rule (memset + distance pass with its fused scoring + reduce pass, with their
+    programmatic-dependent-launch edges) as ONE graph launch and returns `plan.out`.  Every launch
+    of the library is capturable (it never synchronises and allocates nothing).  Worth it where
+    launch latency shows: small d, or a host loop that cannot stay ahead of the GPU. """
+    if self._graph is None:
+      with _on(self.device):
+        self()                                           # warm-up outside the capture (module loading, attributes)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+          stream = torch.cuda.current_stream(self.device).cuda_stream      # the capture stream
+          code = self._fn(*(self._args[:-1] + (stream,)))
+        if code != 0:
+          _lib.check(code, self._what)
+      self._graph = graph
+    graph, out = self._graph, self.out
+    def replay():
+      graph.replay()
+      return out
+    return replay
   def __call__(self):
     if torch.cuda.current_device() == self.device.index:
       code = self._fn(*self._args)

@@ -167,3 +167,19 @@ def test_sharded_plan_brute_and_status():
   want = bz.gars["brute"](gradients=rows, f=3)
   assert torch.equal(plan(), want) and int(plan.status.item()) == 0
   assert plan.selection.cpu().tolist() == bz.last_selection()
+
+@pytest.mark.parametrize("gar,kw", [("krum", dict(f=5)), ("bulyan", dict(f=5)), ("cge", dict(f=5)), ("aksel", dict(f=5)), ("trmean", dict(f=5))])
+def test_plan_graph_replays_the_same_result(gar, kw):
+  """ `Plan.graph()`: the rule captured once in a CUDA graph (memset, fused distance + scoring pass,
+  PDL-launched reduce pass) gives what the direct call gives, replay after replay, and follows
+  in-place updates of the rows. """
+  import byzantinemomentum_b200 as bz
+  rows = [r.to(DEV) for r in _inputs(25, 5, 30011, 93)]
+  plan = bz.Plan(gar, rows, **kw)
+  want = plan().clone()
+  replay = plan.graph()
+  for _ in range(3):
+    assert torch.equal(replay(), want)
+  rows[2].mul_(-2.)
+  want = bz.gars[gar](gradients=rows, **kw)
+  assert torch.equal(replay(), want)

@@ -34,6 +34,45 @@ for gar, n, nb, f, d in CASES:
       best = t if best is None else min(best, t)
     rec["reuse_us" if reuse else "full_us"] = best
   rec["ratio"] = rec["reuse_us"] / rec["full_us"]
+  # the same 16 evaluations through the C ABI with every argument prepared (no Python bookkeeping in
+  # the timed loop): what the library itself gains
+  if gar == "krum":
+    import ctypes
+    from byzantinemomentum_b200 import _lib
+    lib = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    ws = engine._workspace(dev, st)
+    outb = torch.empty(d, device=dev); order = torch.empty(n, dtype=torch.int32, device=dev)
+    tabs = [torch.empty(64 * 64, dtype=torch.float64, device=dev) for _ in range(2)]
+    lists = [honest + [attacks[k]] * nb for k in range(17)]
+    ptrs = [(ctypes.c_void_p * n)(*[g.data_ptr() for g in l]) for l in lists]
+    old = (ctypes.c_int32 * n)(*([i for i in range(n - nb)] + [-1] * nb))
+    mode = ctypes.c_int(0)
+    m = n - f - 2
+    def full(k):
+      return lib.bz_krum(ptrs[k], n, f, m, d, outb.data_ptr(), order.data_ptr(), ws.data_ptr(), ws.numel(), st)
+    def reuse(k, cur):
+      return lib.bz_krum_reuse(ptrs[k], n, f, m, d, outb.data_ptr(), order.data_ptr(), old, tabs[cur].data_ptr(), n - nb + 1,
+                               tabs[cur ^ 1].data_ptr(), ctypes.byref(mode), ws.data_ptr(), ws.numel(), st)
+    for name in ("abi_full_us", "abi_reuse_us"):
+      best = None
+      for rep in range(5):
+        lib.bz_krum_reuse(ptrs[16], n, f, m, d, outb.data_ptr(), order.data_ptr(), None, None, 0, tabs[0].data_ptr(), ctypes.byref(mode),
+                          ws.data_ptr(), ws.numel(), st)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        cur = 0
+        for k in range(16):
+          if name == "abi_full_us": full(k)
+          else:
+            reuse(k, cur); cur ^= 1
+        b.record(); torch.cuda.synchronize()
+        t = a.elapsed_time(b) / 16 * 1e3
+        best = t if best is None else min(best, t)
+      rec[name] = best
+    rec["abi_ratio"] = rec["abi_reuse_us"] / rec["abi_full_us"]
+    rec["abi_last_mode"] = mode.value
   out.append(rec)
   print(json.dumps(rec), flush=True)
 engine.config.reuse_distances = True
