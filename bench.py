@@ -41,7 +41,7 @@ L2_BYTES = 126 * 1024 * 1024
 FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md, used only without MEASURED_PEAKS.json
 
 # kernels of libbyzagg launched per aggregation call (single device)
-LAUNCHES = dict(average=1, median=1, trmean=1, phocas=1, meamed=1, krum=3, bulyan=3, brute=3, aksel=4, cge=3)
+LAUNCHES = dict(average=1, median=1, trmean=1, phocas=1, meamed=1, krum=2, bulyan=2, brute=2, aksel=3, cge=2)
 
 def algorithmic_bytes(gar, n, f, d, m=None):
   """ bytes one call must move, per GAR (no credit for aliases or L2 hits). """
@@ -274,9 +274,11 @@ def timed_max_over_ranks(torch, dist, device, fn, steps, warmup=5):
 def sharded_block(torch, dist, bz, sharded, device, world, rank, peak):
   """ The multi-GPU path BASELINE.json's north_star names, timed on the device:
     collective  Multi-Krum + Bulyan at C3 (n = 25, f = 5, d = 1,310,922 PER GPU: weak scaling)
-                through the prepared three-phase call, with the NCCL all-gather of the R
-                n x n blocks and with the blocks read in place over NVLink peer memory; beside
-                the same rule on one GPU without any exchange (engine.Plan) in the same process;
+                through the prepared sharded call: with the NCCL all-gather of the R n x n blocks
+                ("nccl"), with the blocks read in place over NVLink peer memory by the selection
+                kernel after a device barrier ("p2p"), and with the exchange INSIDE the distance
+                pass ("fused": bz_krum_peers, two launches per step); beside the same rule on one GPU
+                without any exchange (engine.Plan) in the same process;
     c4_strong   median + trimmed mean at C4 (n = 51, f = 12, d = 36,546,980 TOTAL, split over the
                 N ranks: strong scaling; no collective on this path). """
   out = dict(world=world)
@@ -291,7 +293,7 @@ def sharded_block(torch, dist, bz, sharded, device, world, rank, peak):
     rec = dict(gar=gar, n=n, f=f, d_per_gpu=d, steps=steps)
     local = [bz.Plan(gar, st, f=f) for st in stacks]
     rec["single_gpu_us"] = timed_max_over_ranks(torch, dist, device, lambda k: local[k % sets](), steps)
-    for exchange in ("nccl", "p2p"):
+    for exchange in ("nccl", "p2p", "fused"):
       try:
         plans = [sharded.ShardedPlan(gar, st, f=f, exchange=exchange) for st in stacks]
         rec[exchange + "_us"] = timed_max_over_ranks(torch, dist, device, lambda k: plans[k % sets](), steps)
@@ -300,7 +302,7 @@ def sharded_block(torch, dist, bz, sharded, device, world, rank, peak):
       except Exception as err:
         rec[exchange + "_error"] = f"{type(err).__name__}: {err}"[:200]
     alg = (n + (n - f - 2) + 1) * d * 4
-    best = min(rec.get("nccl_us", math.inf), rec.get("p2p_us", math.inf))
+    best = min(rec.get("nccl_us", math.inf), rec.get("p2p_us", math.inf), rec.get("fused_us", math.inf))
     if math.isfinite(best):
       rec["aggregate_gbs"] = world * alg / (best * 1e-6) / 1e9
       rec["hbm_frac_per_gpu"] = alg / (best * 1e-6) / 1e9 / peak
@@ -462,7 +464,7 @@ def run_b200(args):
   e2e = dict(value=world * d / (e2e_ms * 1e-3), unit="params/s", h2d_bytes_per_step=n * d * 4, d2h_bytes_per_step=d * 4,
              h2d_probe=probe, pcie_floor_ms=probe.get("ms"), h2d_rate_achieved_gbs=n * d * 4 / (e2e_ms * 1e-3) / 1e9,
              note="pcie_floor_ms = one contiguous pinned 131 MB copy on THIS box (PCIe Gen5 x16 nominal: 2.1-2.4 ms); the step adds the kernel (~25 us), the 5 MB result copy and its synchronisation",
-             ms_per_step=e2e_ms, steps=e2e_steps, host_buffers="pinned" + (", allocated on the GPU-local NUMA node" if numa_local else ""), call=f"byzantinemomentum_b200.gars[{gar!r}].unchecked(gradients=<{n} pinned host tensors>, f={f})")
+             ms_per_step=e2e_ms, steps=e2e_steps, host_buffers="pinned" + (", allocated under the NVML ideal-affinity binding" if numa_local else "") + "; staged over 4 copy streams", call=f"byzantinemomentum_b200.gars[{gar!r}].unchecked(gradients=<{n} pinned host tensors>, f={f})")
   del host
 
   line = dict(metric="aggregated-params/sec", value=value, unit="params/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),

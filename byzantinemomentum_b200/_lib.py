@@ -18,6 +18,7 @@ MAX_N = 64
 MAX_PEERS = 16
 STATUS_NO_FINITE_SET = 1
 STATUS_DEGENERATE = 2
+STATUS_PEER_TIMEOUT = 3
 STATUS_MESSAGES = {
   STATUS_NO_FINITE_SET: "Too many non-finite gradients: a non-Byzantine gradient must only contain finite coordinates",
   STATUS_DEGENERATE: "Too many non-finite scores: fewer finite Multi-Krum scores than gradients to average",
@@ -53,6 +54,8 @@ SIGNATURES = {
   "bz_krum_reuse": (_i, [_c_rows, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
   "bz_bulyan_reuse": (_i, [_c_rows, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
   "bz_brute_reuse": (_i, [_c_rows, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+  "bz_krum_peers": (_i, [_c_rows, _i, _i, _i, _i64, _vp, _vp, _vp, _i, _i, _c_rows, _c_rows, ctypes.c_uint, _vp, _sz, _vp]),
+  "bz_bulyan_peers": (_i, [_c_rows, _i, _i, _i, _i64, _vp, _vp, _vp, _i, _i, _c_rows, _c_rows, ctypes.c_uint, _vp, _sz, _vp]),
   "bz_aksel": (_i, [_c_rows, _i, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
   "bz_cge": (_i, [_c_rows, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
   "bz_pairdist_partial": (_i, [_c_rows, _i, _i64, _vp, _vp, _sz, _vp]),

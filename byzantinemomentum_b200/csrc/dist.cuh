@@ -54,6 +54,11 @@ struct SelectTail {
   int u_old;
   double* cache_out;
   int reused;
+  // fused exchange over peer memory (bz_*_peers): nranks > 0
+  int nranks, rank;
+  unsigned epoch;
+  double* const* peer_blocks;
+  unsigned* const* peer_flags;
 };
 int launch_pairdist_ring(const RowTable& rows, int n, int64_t d, double* parts, cudaStream_t st,
                          const unsigned char* self_rows, int nself, SelectTail* select = nullptr);

@@ -31,6 +31,7 @@
 
 #include "dist.cuh"
 #include "k5_device.cuh"
+#include "launch.cuh"
 #include "reduce.cuh"
 #include "tma.cuh"
 
@@ -77,7 +78,29 @@ struct RingTail {
   double* cache_out;
   int u_old;
   signed char old_index[kMaxN];
+  // Exchange fused into this launch (d-sharded path, one process per GPU): the last CTA writes the rank's
+  // reduced block into its slot of a buffer mapped on every GPU (peer memory over NVLink), raises its flag
+  // in every peer's flag array, waits for the peers' flags, then adds the R blocks IN PLACE from the R GPUs
+  // (plain loads on peer addresses, rank order: bitwise the same table on every rank) and scores.
+  int nranks, rank;                       // nranks == 0: single GPU
+  unsigned epoch;                         // step number, > the previous step's
+  double* peer_block[BZ_MAX_PEERS];       // this step's slot on every rank ([rank] is local)
+  unsigned* peer_flag[BZ_MAX_PEERS];      // this step's flag array (nranks words) on every rank
 };
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p) {     // never from a stale L1 line (the slot is rewritten every other step)
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
 
 // New rows of a reuse call: star task = one new row against 25 consecutive rows.
 constexpr int kStarMax = 4;
@@ -85,7 +108,9 @@ struct StarList {
   unsigned char row[kStarMax];
   int count;                // 0: the ordinary pass over all pairs
   int slots;                // rows per star task: 3 or 25
+  int list_k;               // > 0: small n, the ordinary pass as LIST tasks of list_k pairs per warp (see sweep_list)
 };
+constexpr int kListMax = 16;
 
 // ---- cluster helpers -------------------------------------------------------------------------
 __device__ __forceinline__ unsigned cluster_ctarank() {
@@ -109,7 +134,7 @@ __device__ __forceinline__ void mbar_arrive_remote(unsigned long long* bar, unsi
 // composite 2k covers diagonal blocks 5k, 5k+1 (whole) and the identity 5-cycle of 5k+2,
 // composite 2k+1 covers 5k+3, 5k+4 (whole) and the second 5-cycle of 5k+2.
 struct Task {
-  int kind;        // 0 = none, 1 = OFF, 2 = COMP, 3 = STAR
+  int kind;        // 0 = none, 1 = OFF, 2 = COMP, 3 = STAR, 4 = LIST (g0 = first pair id, g1 = pair count)
   int g0, g1, g2;  // OFF: (ga, gb, -); COMP: (X, Y, Z) group indices, -1 = absent; STAR: (pivot row, first group, -)
   int perm;        // COMP: Z rows walked in the order 0,2,4,1,3
 };
@@ -250,6 +275,36 @@ __device__ __forceinline__ void sweep_star(const float* x_base, const float* r_b
   }
 }
 
+// LIST: up to kListMax arbitrary pairs (row offsets in registers), two loads per pair.  For n <= 20 a
+// 25-slot block per warp leaves most of the 12 warps idle and the pass costs the same per tile
+// whatever n (37 us at n = 11, d = 1.31M for 9 us of HBM time): the n(n-1)/2 pairs are dealt out evenly
+// instead, ceil(P / 12) per warp.  Twice the shared-memory reads per pair of a block task — irrelevant
+// where HBM is the bound.  Same per-pair operation sequence as every other task: bit-identical sums.
+template <int T>
+__device__ __forceinline__ void sweep_list(const float* buf, const int (&oa)[kListMax], const int (&ob)[kListMax], int count, int lane,
+                                           u64 (&acc)[kRSlots]) {
+#pragma unroll
+  for (int c = 0; c < T; c += 128) {
+    const int o = c + lane * 4;
+#pragma unroll
+    for (int p = 0; p < kListMax; ++p) {
+      if (p < count) {
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(buf + oa[p] + o);
+        const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(buf + ob[p] + o);
+        const u64 d0 = sub2(a.x, b.x), d1 = sub2(a.y, b.y);
+        acc[p] = fma2(d0, d0, acc[p]);
+        acc[p] = fma2(d1, d1, acc[p]);
+      }
+    }
+  }
+}
+// pair id q (row-major over i < j) -> (i, j)
+__device__ __forceinline__ void unrank_pair(int q, int n, int& i, int& j) {
+  i = 0;
+  while (q >= n - 1 - i) { q -= n - 1 - i; ++i; }
+  j = i + 1 + q;
+}
+
 template <int T>
 __device__ __forceinline__ void sweep_self(const float* stage, const int (&srow)[kSelfPerWarp], int nself, int lane, u64 (&facc)[kSelfPerWarp]) {
 #pragma unroll
@@ -292,12 +347,13 @@ __device__ __forceinline__ void ring_stage_tail(float* buf, const RowTable& rows
 
 // One CTA = 12 warps = 12 tasks; a cluster of C CTAs covers tasks [0, 12 C) of the same tiles.
 // parts[cluster * n * n + i * n + j] (i < j; i == j for the rows of `self`).
-template <int T, int STAGES, bool SELF, bool CLUSTER>
+template <int T, int STAGES, bool SELF, bool CLUSTER, bool LIST>
 __global__ void __launch_bounds__(kRThreads, 1)
 k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList self, const __grid_constant__ RingTail tail,
         const __grid_constant__ StarList star, const int n, const int csize, const int64_t d, const int64_t nfull,
         double* __restrict__ parts) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  pdl_trigger();                     // K3 / K4 may be scheduled while this grid drains (they wait for its completion)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ng = (n + kG - 1) / kG;
   const int rows_alloc = ng * kG;
@@ -311,7 +367,20 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
   const int nclusters = CLUSTER ? (int)(gridDim.x / C) : (int)gridDim.x;
 
   Task task;
-  if (star.count == 0) {
+  int la[LIST ? kListMax : 1], lb[LIST ? kListMax : 1];     // LIST is its own instantiation: the block kernels keep their registers
+#pragma unroll
+  for (int p = 0; p < (LIST ? kListMax : 1); ++p) { la[p] = 0; lb[p] = 0; }
+  if (LIST) {
+    const int npairs = n * (n - 1) / 2, first = (rank * kRWarps + warp) * star.list_k;
+    task = Task{0, first, 0, -1, 0};
+    if (first < npairs) {
+      task.kind = 4;
+      task.g1 = min(star.list_k, npairs - first);
+#pragma unroll
+      for (int p = 0; p < (LIST ? kListMax : 1); ++p)
+        if (p < task.g1) { int i, j; unrank_pair(first + p, n, i, j); la[p] = i * T; lb[p] = j * T; }
+    }
+  } else if (star.count == 0) {
     task = make_task(rank * kRWarps + warp, ng);
   } else {
     // reuse call: star task t = (new row t / chunks, rows [slots (t % chunks), + slots)); g1 = first ROW here
@@ -390,8 +459,8 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
       if (gw + q * kRWarps * C < self.count) { srow[q] = self.row[gw + q * kRWarps * C]; nself = q + 1; }
   }
   // shared-memory offsets of the task's row groups (absent groups read group 0: discarded)
-  const int o0 = task.kind == 3 ? task.g0 * T : (task.g0 >= 0 ? task.g0 : 0) * kG * T;
-  const int o1 = task.kind == 3 ? task.g1 * T : (task.g1 >= 0 ? task.g1 : 0) * kG * T;
+  const int o0 = task.kind == 4 ? 0 : task.kind == 3 ? task.g0 * T : (task.g0 >= 0 ? task.g0 : 0) * kG * T;
+  const int o1 = task.kind == 4 ? 0 : task.kind == 3 ? task.g1 * T : (task.g1 >= 0 ? task.g1 : 0) * kG * T;
   const int star_valid = task.kind == 3 ? min(star.slots, n - task.g1) : 0;
   const int o2 = (task.g2 >= 0 ? task.g2 : 0) * kG * T;
   // fp32 terms per accumulator half between two flushes into fp64 (a tile adds T / 64 of them)
@@ -404,11 +473,15 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
   for (int k = 0; k < mine; ++k) {
     mbar_wait(&full[s], parity);
     const float* buf = stages + (size_t)s * stage_floats;
-    if (task.kind == 1)      sweep_off<T>(buf + o0, buf + o1, lane, acc);
-    else if (task.kind == 2) sweep_comp<T>(buf + o0, buf + o1, buf + o2, task.perm, lane, acc);
-    else if (task.kind == 3) {
-      if (star.slots == 3) sweep_star<T, 3>(buf + o0, buf + o1, star_valid, lane, acc);
-      else                 sweep_star<T, kRSlots>(buf + o0, buf + o1, star_valid, lane, acc);
+    if constexpr (LIST) {
+      if (task.kind == 4) sweep_list<T>(buf, la, lb, task.g1, lane, acc);
+    } else {
+      if (task.kind == 1)      sweep_off<T>(buf + o0, buf + o1, lane, acc);
+      else if (task.kind == 2) sweep_comp<T>(buf + o0, buf + o1, buf + o2, task.perm, lane, acc);
+      else if (task.kind == 3) {
+        if (star.slots == 3) sweep_star<T, 3>(buf + o0, buf + o1, star_valid, lane, acc);
+        else                 sweep_star<T, kRSlots>(buf + o0, buf + o1, star_valid, lane, acc);
+      }
     }
     if (SELF && nself > 0) sweep_self<T>(buf, srow, nself, lane, facc);
     __syncwarp();
@@ -439,11 +512,15 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    if (task.kind == 1)      sweep_off<T>(stages + o0, stages + o1, lane, acc);
-    else if (task.kind == 2) sweep_comp<T>(stages + o0, stages + o1, stages + o2, task.perm, lane, acc);
-    else if (task.kind == 3) {
-      if (star.slots == 3) sweep_star<T, 3>(stages + o0, stages + o1, star_valid, lane, acc);
-      else                 sweep_star<T, kRSlots>(stages + o0, stages + o1, star_valid, lane, acc);
+    if constexpr (LIST) {
+      if (task.kind == 4) sweep_list<T>(stages, la, lb, task.g1, lane, acc);
+    } else {
+      if (task.kind == 1)      sweep_off<T>(stages + o0, stages + o1, lane, acc);
+      else if (task.kind == 2) sweep_comp<T>(stages + o0, stages + o1, stages + o2, task.perm, lane, acc);
+      else if (task.kind == 3) {
+        if (star.slots == 3) sweep_star<T, 3>(stages + o0, stages + o1, star_valid, lane, acc);
+        else                 sweep_star<T, kRSlots>(stages + o0, stages + o1, star_valid, lane, acc);
+      }
     }
     if (SELF && nself > 0) sweep_self<T>(stages, srow, nself, lane, facc);
     pending = 1;
@@ -474,6 +551,9 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
       if (ri < n && rj < n) block[(size_t)ri * n + rj] = dacc;
     }
   }
+  else if (task.kind == 4) {
+    if (lane < task.g1) { int i, j; unrank_pair(task.g0 + lane, n, i, j); block[(size_t)i * n + j] = dacc; }
+  }
   else if (task.kind == 3) {
     const int r = task.g1 + lane;
     if (lane < star_valid && r != task.g0) block[(size_t)min(r, task.g0) * n + max(r, task.g0)] = dacc;
@@ -497,6 +577,8 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
     // and the last group to finish sums the <= 10 group blocks and runs the selection in the
     // shared memory the ring no longer needs (every other CTA is past its ring by then).
     __shared__ int elected;
+    __shared__ int peer_timeout;
+    if (threadIdx.x == 0) peer_timeout = 0;
     const int len = n * n;
     const int ngroups = (nclusters + kTailGroup - 1) / kTailGroup;
     const int group = cluster_id / kTailGroup;
@@ -539,6 +621,36 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
           // scoring code expects it; diagonal entries (alias flags) always come from this pass.
           const int N = tail.n;
           double* table = sm + (n == N ? 0 : (size_t)N * N);
+          if (tail.nranks > 0) {
+            // ---- exchange over peer memory, inside this launch ----
+            double* mine = tail.peer_block[tail.rank];
+            for (int e = threadIdx.x; e < len; e += kRThreads) {
+              const int i = e / n, j = e - i * n;
+              double v = 0.;
+              if (i <= j)
+                for (int g = 0; g < ngroups; ++g) v += __ldcg(gblocks + (size_t)g * len + e);
+              mine[e] = v;
+            }
+            __threadfence_system();
+            __syncthreads();
+            if ((int)threadIdx.x < tail.nranks) {
+              st_release_sys(tail.peer_flag[threadIdx.x] + tail.rank, tail.epoch);       // "rank's block of step `epoch` is there"
+              const unsigned* wait_on = tail.peer_flag[tail.rank] + threadIdx.x;
+              // bounded wait (~2 s): a peer that never shows up must not hang the GPU; the status word says so
+              unsigned spins = 0;
+              while ((int)(ld_acquire_sys(wait_on) - tail.epoch) < 0) {
+                __nanosleep(100);
+                if (++spins > (1u << 24)) { peer_timeout = 1; break; }
+              }
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < len; e += kRThreads) {
+              double v = 0.;
+              for (int r = 0; r < tail.nranks; ++r) v += ld_volatile_f64(tail.peer_block[r] + e);
+              table[e] = v;
+            }
+            __syncthreads();
+          } else
           for (int e = threadIdx.x; e < len; e += kRThreads) {
             const int i = e / n, j = e - i * n;
             double v = 0.;
@@ -557,6 +669,8 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
           if (tail.kind == 3) brute_from_table(tail.map, N, tail.f, tail.total, tail.order, tail.status, sm);
           else                score_from_table(tail.map, N, tail.count, tail.order, tail.kind == 2 ? tail.status : nullptr,
                                                tail.f, tail.m, tail.kind == 2 ? 1 : 0, sm);
+          __syncthreads();
+          if (threadIdx.x == 0 && peer_timeout && tail.status != nullptr) *tail.status = BZ_STATUS_PEER_TIMEOUT;
         }
         if (threadIdx.x <= ngroups) tail.ticket[threadIdx.x] = 0u;
       }
@@ -567,12 +681,12 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
 
 // ---- host side -------------------------------------------------------------------------------
 
-template <int T, int STAGES, bool SELF, bool CLUSTER>
+template <int T, int STAGES, bool SELF, bool CLUSTER, bool LIST = false>
 static int launch_ring_cfg(const RowTable& rows, const SelfList& self, RingTail& tail, const StarList& star, int n, int C, int64_t d,
                            double* parts, cudaStream_t st) {
   const int ng = (n + kG - 1) / kG;
   const size_t smem = (size_t)STAGES * ng * kG * T * sizeof(float) + 2 * STAGES * sizeof(unsigned long long);
-  auto kernel = k2_ring<T, STAGES, SELF, CLUSTER>;
+  auto kernel = k2_ring<T, STAGES, SELF, CLUSTER, LIST>;
   static unsigned long long opted = 0;
   static int max_clusters[64][kRMaxCluster + 1] = {};
   int dev = 0;
@@ -660,6 +774,13 @@ int launch_pairdist_ring(const RowTable& rows, int n, int64_t d, double* parts, 
     tail.cache_out = select->cache_out;
     tail.u_old = select->u_old;
     select->reused = 0;
+    if (select->nranks > 0) {
+      tail.nranks = select->nranks; tail.rank = select->rank; tail.epoch = select->epoch;
+      for (int r = 0; r < BZ_MAX_PEERS; ++r) {
+        tail.peer_block[r] = select->peer_blocks[r < select->nranks ? r : 0];
+        tail.peer_flag[r] = select->peer_flags[r < select->nranks ? r : 0];
+      }
+    }
     // Distance reuse: unique row k was row old_index[k] of the table in `cache_in`.  A star pass is
     // taken when 1..kStarMax unique rows are new, every other one is in the table, and that table
     // came out of the same launch geometry (tile width, cluster size: functions of the row count) —
@@ -694,11 +815,19 @@ int launch_pairdist_ring(const RowTable& rows, int n, int64_t d, double* parts, 
       }
     }
   }
+  {
+    // small n: deal the pairs out evenly instead of 25-slot blocks (BYZAGG_K2_NOLIST=1: blocks, for A/B runs)
+    const char* nolist = getenv("BYZAGG_K2_NOLIST");
+    const int npairs = n * (n - 1) / 2, per = (npairs + kRWarps - 1) / kRWarps;
+    if (C == 1 && star.count == 0 && n >= 2 && per <= kListMax && n <= 20 && !(nolist && nolist[0] == '1')) star.list_k = per;
+  }
 #define BZ_RING(T, S, CL) (selfk ? launch_ring_cfg<T, S, true, CL>(rows, self, tail, star, n, C, d, parts, st) : launch_ring_cfg<T, S, false, CL>(rows, self, tail, star, n, C, d, parts, st))
   int nparts;
   if (C == 1) {
     if (rows_alloc > 25) return -1;
-    nparts = BZ_RING(512, 4, false);
+    if (star.list_k > 0) nparts = selfk ? launch_ring_cfg<512, 4, true, false, true>(rows, self, tail, star, n, C, d, parts, st)
+                                        : launch_ring_cfg<512, 4, false, false, true>(rows, self, tail, star, n, C, d, parts, st);
+    else                 nparts = BZ_RING(512, 4, false);
   } else if (rows_alloc <= 35) nparts = BZ_RING(512, 3, true);
   else                         nparts = BZ_RING(256, 3, true);   // (512-column tiles with 2 stages measured 20 % slower at n = 40...51)
 #undef BZ_RING

@@ -12,6 +12,7 @@
 // Roofline: HBM, n·4 B per coordinate (+4 B for the centre).
 #include "dist.cuh"
 #include "k5_device.cuh"
+#include "launch.cuh"
 #include "reduce.cuh"
 
 namespace bz {
@@ -26,6 +27,7 @@ __global__ void __launch_bounds__(kRdThreads, 2)
 k2_rowdist(const __grid_constant__ RowTable rows, const int n, const float* __restrict__ center, const Geom g,
            double* __restrict__ parts, int32_t* __restrict__ order, unsigned* __restrict__ ticket, const int sqrt_norm) {
   __shared__ double warp_tot[kRdWarps][kMaxN];
+  pdl_trigger();                     // the K3 pass may be scheduled while this grid drains
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float acc[kMaxN];
 #pragma unroll

@@ -13,6 +13,11 @@ namespace bz {
 // writes are visible).  Used for the second pass of the distance rules (K3 / K4 after K2 + scoring).
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// In the PRIMARY kernel, at its start: dependents launched with `launch_after` may be scheduled as soon as
+// SM resources free up (they still block in pdl_wait() until this whole grid has completed and flushed).
+// Without it they are only scheduled once every CTA has EXITED — i.e. after the single-CTA scoring tail of
+// the distance pass, which is exactly the latency the dependent launch is meant to hide.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
 template <class... Params, class... Args>
 inline cudaError_t launch_after(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {

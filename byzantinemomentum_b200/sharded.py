@@ -29,7 +29,7 @@ import torch.distributed as dist
 
 from . import engine as _engine
 
-__all__ = ["aggregate", "aggregate_p2p", "compute_avg_dev_max", "replicate", "apply_update", "shard_bounds", "PeerExchange", "ShardedPlan", "COORDINATE_WISE", "DISTANCE_BASED"]
+__all__ = ["aggregate", "aggregate_p2p", "compute_avg_dev_max", "replicate", "apply_update", "shard_bounds", "PeerExchange", "FusedExchange", "ShardedPlan", "COORDINATE_WISE", "DISTANCE_BASED"]
 
 COORDINATE_WISE = ("average", "median", "trmean", "phocas", "meamed")
 DISTANCE_BASED = ("krum", "bulyan", "brute", "aksel", "cge")
@@ -81,6 +81,47 @@ def peer_exchange(n, device, group=None):
   ex = _exchanges.get(key)
   if ex is None:
     ex = _exchanges[key] = PeerExchange(n, device, group)
+  return ex
+
+class FusedExchange:
+  """ Symmetric buffer for the exchange that runs INSIDE the distance pass (`bz_krum_peers`,
+  `bz_bulyan_peers`): per rank two slots of n*n doubles plus, per slot, a flag array of 16 words.  The
+  last CTA of each rank's distance pass writes its block into its slot, raises its flag on every GPU,
+  waits for the R flags, and adds the R blocks in place over NVLink — no barrier op, no collective, no
+  separate selection kernel.  `epoch` (the step number) tells this step's flags from older ones; two
+  slots make that enough (a rank rewrites slot s only after every peer has signalled the step in
+  between, i.e. finished reading s). """
+  FLAG_WORDS = 16
+  def __init__(self, n, device, group=None):
+    import torch.distributed._symmetric_memory as symm_mem
+    self.n, self.device = n, device
+    self.group = group if group is not None else dist.group.WORLD
+    self.world = dist.get_world_size(self.group)
+    self.rank = dist.get_rank(self.group)
+    words = 2 * n * n + 2 * self.FLAG_WORDS // 2             # doubles; the flags are uint32 pairs in the tail
+    self.buffer = symm_mem.empty(words, dtype=torch.float64, device=device)
+    self.buffer.zero_()
+    self.handle = symm_mem.rendezvous(self.buffer, self.group)
+    torch.cuda.synchronize(device)
+    self.handle.barrier(channel=0)                           # every rank's flags are zero before anyone signals
+    torch.cuda.synchronize(device)
+    self.peer_base = [int(p) for p in self.handle.buffer_ptrs]
+    self.epoch = 0
+  def tables(self, slot):
+    """ (ctypes array of the R block pointers, ctypes array of the R flag-array pointers) of a slot. """
+    import ctypes
+    block = slot * self.n * self.n * 8
+    flags = 2 * self.n * self.n * 8 + slot * self.FLAG_WORDS * 4
+    return ((ctypes.c_void_p * self.world)(*[b + block for b in self.peer_base]),
+            (ctypes.c_void_p * self.world)(*[b + flags for b in self.peer_base]))
+
+_fused = {}
+
+def fused_exchange(n, device, group=None):
+  key = (n, device.index, id(group))
+  ex = _fused.get(key)
+  if ex is None:
+    ex = _fused[key] = FusedExchange(n, device, group)
   return ex
 
 def aggregate_p2p(gar, gradients, f=None, m=None, mode="mid", group=None, return_selection=False):
@@ -138,7 +179,11 @@ class ShardedPlan:
             "p2p"   the block is written straight into this rank's slot of a SYMMETRIC buffer, one
                     device-side barrier, and the selection kernel reads the R blocks in place from
                     the R peers over NVLink (`bz_*_select_peers`): gather + scoring in one kernel;
-            "auto"  "p2p" when symmetric memory can be set up for the group, else "nccl".
+            "fused" (krum, bulyan) the exchange runs INSIDE the distance pass: its last CTA publishes the
+                    block in the symmetric buffer, flags the peers, waits for theirs and scores — a step
+                    is the single-GPU rule's two launches, nothing else (`bz_krum_peers`);
+            "auto"  "fused" where it applies, else "p2p", when symmetric memory can be set up for the
+                    group; else "nccl".
   Both exchanges use the same fixed summation order: bitwise identical selections on every rank.
   Coordinate-wise rules need no exchange and simply wrap `engine.Plan`. """
   def __init__(self, gar, gradients, f=None, m=None, mode="mid", group=None, exchange="auto"):
@@ -176,19 +221,40 @@ class ShardedPlan:
     pair = gar in ("krum", "bulyan", "brute")
     width = n * n if pair else n
     # ---- exchange -------------------------------------------------------------------------------
+    fusable = gar in ("krum", "bulyan") and all(g.data_ptr() % 16 == 0 for g in self.rows)
     if exchange == "auto":
       exchange = "nccl"
       if self.world > 1 and self.world <= _lib.MAX_PEERS:
         try:
-          self._ex = peer_exchange(n, device, group)
-          exchange = "p2p"
+          if fusable:
+            self._fx = fused_exchange(n, device, group)
+            exchange = "fused"
+          else:
+            self._ex = peer_exchange(n, device, group)
+            exchange = "p2p"
         except Exception:
           exchange = "nccl"
+    elif exchange == "fused":
+      if not fusable or self.world < 1:
+        raise ValueError("the fused exchange serves krum / bulyan on 16-byte aligned rows")
+      self._fx = fused_exchange(n, device, group)
     elif exchange == "p2p":
       self._ex = peer_exchange(n, device, group)
     elif exchange != "nccl":
       raise ValueError(f"unknown exchange {exchange!r}")
     self.exchange = exchange
+    if exchange == "fused":
+      fx = self._fx
+      mm = n - f - 2 if m is None else m
+      self.status = self._meta[n:]
+      fn = lib.bz_krum_peers if gar == "krum" else lib.bz_bulyan_peers
+      self._fused_fn = fn
+      self._fused_tables = [fx.tables(0), fx.tables(1)]
+      self._fused_head = (self._ptrs, n, int(f), int(mm), d, o, meta, status, fx.rank, fx.world)
+      self._fused_tail = (ws, wn, st)
+      self._check = _lib.check
+      self._pre = None
+      return
     if exchange == "p2p":
       ex = self._ex
       # two slots -> two prepared argument sets; the step counter of the exchange picks one
@@ -249,6 +315,13 @@ class ShardedPlan:
     if self._local is not None:
       return self._local()
     check = self._check
+    if self.exchange == "fused":
+      fx = self._fx
+      fx.epoch += 1
+      blocks, flags = self._fused_tables[fx.epoch % 2]
+      with _engine._on(self.device):
+        check(self._fused_fn(*self._fused_head, blocks, flags, fx.epoch, *self._fused_tail), "bz_*_peers")
+      return self.out
     with _engine._on(self.device):
       if self._pre is not None:
         check(self._pre[0](*self._pre[1]), "bz_median")

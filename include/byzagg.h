@@ -57,6 +57,7 @@ extern "C" {
 #define BZ_STATUS_OK            0
 #define BZ_STATUS_NO_FINITE_SET 1  /* brute: every subset holds a non-finite distance (brute.py:67 assert) */
 #define BZ_STATUS_DEGENERATE    2  /* bulyan: too few finite scores (bulyan.py:70 fails on gradients[None]) */
+#define BZ_STATUS_PEER_TIMEOUT  3  /* bz_*_peers: a peer's block did not arrive within ~2 s (the result is garbage) */
 
 /* Aksel modes (aggregators/aksel.py:43-48) */
 #define BZ_AKSEL_MID 0   /* c = (n + 1) / 2 */
@@ -124,6 +125,28 @@ BZ_API int bz_bulyan_reuse(const float* const* rows, int n, int f, int m, int64_
 BZ_API int bz_brute_reuse(const float* const* rows, int n, int f, int64_t d, float* out, int32_t* sel,
                           int32_t* status, const int32_t* old_index, const double* cache_in, int u_old,
                           double* cache_out, int* mode_out, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- Whole distance rules on a d-shard with the exchange INSIDE the distance pass (one process per GPU)
+ * The rank's n x n block of partial squared distances is written by the last CTA of the distance pass
+ * straight into this rank's slot of a buffer that is mapped on every GPU (peer memory over NVLink /
+ * NVSwitch, e.g. torch symmetric memory); the same CTA raises a flag in every peer's flag array, waits for
+ * the peers' flags and adds the R blocks in place from the R GPUs (rank order: bitwise the same table,
+ * hence the same selection, on every rank), scores, selects; the reduce pass over the local shard
+ * follows by programmatic dependent launch.  Two launches per step, no collective call, no host sync.
+ *   rank, nranks   this process; 1 <= nranks <= BZ_MAX_PEERS
+ *   peer_blocks    HOST array of nranks DEVICE pointers: the slot of THIS step on every rank (n*n doubles
+ *                  each; [rank] is the local one).  Alternate between two slots from step to step.
+ *   peer_flags     HOST array of nranks DEVICE pointers: the flag array (nranks uint32) of this step's
+ *                  slot on every rank; zero before the first step
+ *   epoch          step number: strictly increasing, the same on every rank for the same step
+ *   status         DEVICE int32, required: BZ_STATUS_PEER_TIMEOUT when a peer did not show up
+ * Rows must be 16-byte aligned (the ring kernel); otherwise BZ_EUNSUPPORTED: use the phases below. */
+BZ_API int bz_krum_peers(const float* const* rows, int n, int f, int m, int64_t d, float* out, int32_t* order,
+                         int32_t* status, int rank, int nranks, double* const* peer_blocks,
+                         unsigned* const* peer_flags, unsigned epoch, void* ws, size_t ws_bytes, void* stream);
+BZ_API int bz_bulyan_peers(const float* const* rows, int n, int f, int m, int64_t d, float* out, int32_t* order,
+                           int32_t* status, int rank, int nranks, double* const* peer_blocks,
+                           unsigned* const* peer_flags, unsigned epoch, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- Phases for the d-sharded multi-GPU path ------------------------
  * Each rank runs phase A on its shard, the R partial blocks are all-gathered (one small

@@ -44,10 +44,17 @@ def main():
     same_plan = same_plan and torch.equal(plan_p(), a) and torch.equal(plan_p(), a)       # both slots of the symmetric buffer
     ok = ok and same_plan
     t_plan_n, t_plan_p = timeit(plan_n, 200), timeit(plan_p, 200)
+    t_plan_f = float("nan")
+    if gar in ("krum", "bulyan"):
+      plan_f = sharded.ShardedPlan(gar, rows, f=f, exchange="fused")
+      same_f = all(torch.equal(plan_f(), a) for _ in range(4)) and torch.equal(plan_f.selection, sa[:plan_f.selection.numel()]) and int(plan_f.status.item()) == 0
+      same_plan = same_plan and same_f
+      ok = ok and same_f
+      t_plan_f = timeit(plan_f, 200)
     single = bz.Plan(gar, rows, f=f)
     t_single = timeit(single, 200)
     if rank == 0:
-      print(f"{gar:7s} N={world}: identical={same} plans={same_plan}  aggregate: nccl {t_nccl:7.1f} p2p {t_p2p:7.1f} | ShardedPlan: nccl {t_plan_n:7.1f} p2p {t_plan_p:7.1f} | single-GPU Plan {t_single:7.1f} us/step", flush=True)
+      print(f"{gar:7s} N={world}: identical={same} plans={same_plan}  aggregate: nccl {t_nccl:7.1f} p2p {t_p2p:7.1f} | ShardedPlan: nccl {t_plan_n:7.1f} p2p {t_plan_p:7.1f} fused {t_plan_f:7.1f} | single-GPU Plan {t_single:7.1f} us/step", flush=True)
   flag = torch.tensor([1 if ok else 0], device=dev)
   dist.all_reduce(flag, op=dist.ReduceOp.MIN)
   if rank == 0:
