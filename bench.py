@@ -308,6 +308,16 @@ def sharded_block(torch, dist, bz, sharded, device, world, rank, peak):
       rec["hbm_frac_per_gpu"] = alg / (best * 1e-6) / 1e9 / peak
     rows.append(rec)
     del local
+  # ---- closing the loop: SGD step on the shard + one all-gather of the parameters ----
+  try:
+    params = torch.zeros(world * d, device=device)
+    shard = torch.randn(d, device=device, generator=gen)
+    upd_us = timed_max_over_ranks(torch, dist, device, lambda k: sharded.apply_update(params, shard, 0.01, weight_decay=1e-4), 50)
+    out["model_update"] = dict(what="sharded.apply_update: p -= lr (g + w p) on this rank's d columns, then ONE all-gather of the parameters (experiments/model.py:368-380 for a d-sharded trainer)",
+                               d_total=world * d, us_per_step=upd_us, allgather_bytes_per_rank=d * 4)
+    del params, shard
+  except Exception as err:
+    out["model_update"] = dict(error=f"{type(err).__name__}: {err}"[:200])
   out["collective"] = dict(what="weak scaling: n=25 f=5 d=1,310,922 per GPU; one exchange of R blocks of n*n fp64 per step; us per step, max over ranks",
                            exchange_bytes_per_rank=n * n * 8, rules=rows)
   del stacks

@@ -50,11 +50,11 @@ static void launch_median_n(const RowTable& rows, const Geom& g, float* out, cud
   if (g.vec == 1) {
     static int cache[64] = {0};
     const size_t smem = Stage<N, 1>::kFloats * sizeof(float);
-    k1_median<N, 1><<<persistent_grid(k1_median<N, 1>, smem, g.nv, cache), kK1Threads, smem, st>>>(rows, g, out);
+    launch_after(k1_median<N, 1>, persistent_grid(k1_median<N, 1>, smem, g.nv, cache), kK1Threads, smem, st, rows, g, out);
   } else {
     static int cache[64] = {0};
     const size_t smem = Stage<N, body_vec(N)>::kFloats * sizeof(float);
-    k1_median<N, body_vec(N)><<<persistent_grid(k1_median<N, body_vec(N)>, smem, g.nv, cache), kK1Threads, smem, st>>>(rows, g, out);
+    launch_after(k1_median<N, body_vec(N)>, persistent_grid(k1_median<N, body_vec(N)>, smem, g.nv, cache), kK1Threads, smem, st, rows, g, out);
   }
 }
 
@@ -79,9 +79,9 @@ static void launch_sorted_nv(const RowTable& rows, const Geom& g, int mode, int 
   const size_t stage = Stage<N, VEC>::kFloats * sizeof(float);
   const size_t both = stage + Stage<N, VEC>::kColumnFloats * sizeof(float);
   if (mode == kModeTrmean)
-    k1_sorted<N, VEC, -1, -1><<<persistent_grid(k1_sorted<N, VEC, -1, -1>, stage, g.nv, cache_plain), kK1Threads, stage, st>>>(rows, g, mode, f, out);
+    launch_after(k1_sorted<N, VEC, -1, -1>, persistent_grid(k1_sorted<N, VEC, -1, -1>, stage, g.nv, cache_plain), kK1Threads, stage, st, rows, g, mode, f, out);
   else
-    k1_sorted<N, VEC, -1, -1><<<persistent_grid(k1_sorted<N, VEC, -1, -1>, both, g.nv, cache_closest), kK1Threads, both, st>>>(rows, g, mode, f, out);
+    launch_after(k1_sorted<N, VEC, -1, -1>, persistent_grid(k1_sorted<N, VEC, -1, -1>, both, g.nv, cache_closest), kK1Threads, both, st, rows, g, mode, f, out);
 }
 
 template <int N>
@@ -127,7 +127,7 @@ static void launch_special_nf(const RowTable& rows, const Geom& g, float* out, c
   if (g.nv <= 0) return;
   static int cache[64] = {0};
   const size_t smem = Stage<N, body_vec(N)>::kFloats * sizeof(float);
-  k1_sorted<N, body_vec(N), F, BZ_SPECIAL_MODE><<<persistent_grid(k1_sorted<N, body_vec(N), F, BZ_SPECIAL_MODE>, smem, g.nv, cache), kK1Threads, smem, st>>>(rows, g, BZ_SPECIAL_MODE, F, out);
+  launch_after(k1_sorted<N, body_vec(N), F, BZ_SPECIAL_MODE>, persistent_grid(k1_sorted<N, body_vec(N), F, BZ_SPECIAL_MODE>, smem, g.nv, cache), kK1Threads, smem, st, rows, g, BZ_SPECIAL_MODE, F, out);
 }
 
 bool BZ_SPECIAL_FN(int n, int f, const RowTable& rows, const Geom& g, float* out, cudaStream_t st) {

@@ -75,7 +75,13 @@ template <int N, int VEC, class Body>
 __device__ __forceinline__ void k1_walk(const RowTable& rows, const Geom& g, float* stage, Body body) {
   const int64_t stride = (int64_t)gridDim.x * kK1Threads;
   int64_t v = (int64_t)blockIdx.x * kK1Threads + threadIdx.x;
+  // Programmatic dependent launch on both sides: the NEXT kernel of the stream may be scheduled while this
+  // grid drains, and this one was scheduled while its predecessor drained — the wait below returns once
+  // that predecessor has completed and its writes (possibly these very rows) are visible.  Back-to-back
+  // calls lose the launch gap (~1.5 us of a 24 us pass at d = 1.3M).
+  pdl_trigger();
   if (v >= g.nv) return;
+  pdl_wait();
 #if BZ_K1_VARIANT == 0
   float* col = stage + threadIdx.x * VEC;
   int64_t e0 = v * VEC - g.shift;

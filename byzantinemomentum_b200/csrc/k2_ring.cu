@@ -96,9 +96,12 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ double ld_volatile_f64(const double* p) {     // never from a stale L1 line (the slot is rewritten every other step)
+// Coherent at system scope, never from a stale L1 line (the slot is rewritten every other step); NOT
+// `volatile` asm, so that the R loads of a table entry are issued together (a volatile load per rank made
+// the entry cost R NVLink round trips).
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
   double v;
-  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  asm("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
 
@@ -108,9 +111,7 @@ struct StarList {
   unsigned char row[kStarMax];
   int count;                // 0: the ordinary pass over all pairs
   int slots;                // rows per star task: 3 or 25
-  int list_k;               // > 0: small n, the ordinary pass as LIST tasks of list_k pairs per warp (see sweep_list)
 };
-constexpr int kListMax = 16;
 
 // ---- cluster helpers -------------------------------------------------------------------------
 __device__ __forceinline__ unsigned cluster_ctarank() {
@@ -134,7 +135,7 @@ __device__ __forceinline__ void mbar_arrive_remote(unsigned long long* bar, unsi
 // composite 2k covers diagonal blocks 5k, 5k+1 (whole) and the identity 5-cycle of 5k+2,
 // composite 2k+1 covers 5k+3, 5k+4 (whole) and the second 5-cycle of 5k+2.
 struct Task {
-  int kind;        // 0 = none, 1 = OFF, 2 = COMP, 3 = STAR, 4 = LIST (g0 = first pair id, g1 = pair count)
+  int kind;        // 0 = none, 1 = OFF, 2 = COMP, 3 = STAR
   int g0, g1, g2;  // OFF: (ga, gb, -); COMP: (X, Y, Z) group indices, -1 = absent; STAR: (pivot row, first group, -)
   int perm;        // COMP: Z rows walked in the order 0,2,4,1,3
 };
@@ -275,36 +276,6 @@ __device__ __forceinline__ void sweep_star(const float* x_base, const float* r_b
   }
 }
 
-// LIST: up to kListMax arbitrary pairs (row offsets in registers), two loads per pair.  For n <= 20 a
-// 25-slot block per warp leaves most of the 12 warps idle and the pass costs the same per tile
-// whatever n (37 us at n = 11, d = 1.31M for 9 us of HBM time): the n(n-1)/2 pairs are dealt out evenly
-// instead, ceil(P / 12) per warp.  Twice the shared-memory reads per pair of a block task — irrelevant
-// where HBM is the bound.  Same per-pair operation sequence as every other task: bit-identical sums.
-template <int T>
-__device__ __forceinline__ void sweep_list(const float* buf, const int (&oa)[kListMax], const int (&ob)[kListMax], int count, int lane,
-                                           u64 (&acc)[kRSlots]) {
-#pragma unroll
-  for (int c = 0; c < T; c += 128) {
-    const int o = c + lane * 4;
-#pragma unroll
-    for (int p = 0; p < kListMax; ++p) {
-      if (p < count) {
-        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(buf + oa[p] + o);
-        const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(buf + ob[p] + o);
-        const u64 d0 = sub2(a.x, b.x), d1 = sub2(a.y, b.y);
-        acc[p] = fma2(d0, d0, acc[p]);
-        acc[p] = fma2(d1, d1, acc[p]);
-      }
-    }
-  }
-}
-// pair id q (row-major over i < j) -> (i, j)
-__device__ __forceinline__ void unrank_pair(int q, int n, int& i, int& j) {
-  i = 0;
-  while (q >= n - 1 - i) { q -= n - 1 - i; ++i; }
-  j = i + 1 + q;
-}
-
 template <int T>
 __device__ __forceinline__ void sweep_self(const float* stage, const int (&srow)[kSelfPerWarp], int nself, int lane, u64 (&facc)[kSelfPerWarp]) {
 #pragma unroll
@@ -347,7 +318,7 @@ __device__ __forceinline__ void ring_stage_tail(float* buf, const RowTable& rows
 
 // One CTA = 12 warps = 12 tasks; a cluster of C CTAs covers tasks [0, 12 C) of the same tiles.
 // parts[cluster * n * n + i * n + j] (i < j; i == j for the rows of `self`).
-template <int T, int STAGES, bool SELF, bool CLUSTER, bool LIST>
+template <int T, int STAGES, bool SELF, bool CLUSTER>
 __global__ void __launch_bounds__(kRThreads, 1)
 k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList self, const __grid_constant__ RingTail tail,
         const __grid_constant__ StarList star, const int n, const int csize, const int64_t d, const int64_t nfull,
@@ -367,20 +338,7 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
   const int nclusters = CLUSTER ? (int)(gridDim.x / C) : (int)gridDim.x;
 
   Task task;
-  int la[LIST ? kListMax : 1], lb[LIST ? kListMax : 1];     // LIST is its own instantiation: the block kernels keep their registers
-#pragma unroll
-  for (int p = 0; p < (LIST ? kListMax : 1); ++p) { la[p] = 0; lb[p] = 0; }
-  if (LIST) {
-    const int npairs = n * (n - 1) / 2, first = (rank * kRWarps + warp) * star.list_k;
-    task = Task{0, first, 0, -1, 0};
-    if (first < npairs) {
-      task.kind = 4;
-      task.g1 = min(star.list_k, npairs - first);
-#pragma unroll
-      for (int p = 0; p < (LIST ? kListMax : 1); ++p)
-        if (p < task.g1) { int i, j; unrank_pair(first + p, n, i, j); la[p] = i * T; lb[p] = j * T; }
-    }
-  } else if (star.count == 0) {
+  if (star.count == 0) {
     task = make_task(rank * kRWarps + warp, ng);
   } else {
     // reuse call: star task t = (new row t / chunks, rows [slots (t % chunks), + slots)); g1 = first ROW here
@@ -459,8 +417,8 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
       if (gw + q * kRWarps * C < self.count) { srow[q] = self.row[gw + q * kRWarps * C]; nself = q + 1; }
   }
   // shared-memory offsets of the task's row groups (absent groups read group 0: discarded)
-  const int o0 = task.kind == 4 ? 0 : task.kind == 3 ? task.g0 * T : (task.g0 >= 0 ? task.g0 : 0) * kG * T;
-  const int o1 = task.kind == 4 ? 0 : task.kind == 3 ? task.g1 * T : (task.g1 >= 0 ? task.g1 : 0) * kG * T;
+  const int o0 = task.kind == 3 ? task.g0 * T : (task.g0 >= 0 ? task.g0 : 0) * kG * T;
+  const int o1 = task.kind == 3 ? task.g1 * T : (task.g1 >= 0 ? task.g1 : 0) * kG * T;
   const int star_valid = task.kind == 3 ? min(star.slots, n - task.g1) : 0;
   const int o2 = (task.g2 >= 0 ? task.g2 : 0) * kG * T;
   // fp32 terms per accumulator half between two flushes into fp64 (a tile adds T / 64 of them)
@@ -473,15 +431,11 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
   for (int k = 0; k < mine; ++k) {
     mbar_wait(&full[s], parity);
     const float* buf = stages + (size_t)s * stage_floats;
-    if constexpr (LIST) {
-      if (task.kind == 4) sweep_list<T>(buf, la, lb, task.g1, lane, acc);
-    } else {
-      if (task.kind == 1)      sweep_off<T>(buf + o0, buf + o1, lane, acc);
-      else if (task.kind == 2) sweep_comp<T>(buf + o0, buf + o1, buf + o2, task.perm, lane, acc);
-      else if (task.kind == 3) {
-        if (star.slots == 3) sweep_star<T, 3>(buf + o0, buf + o1, star_valid, lane, acc);
-        else                 sweep_star<T, kRSlots>(buf + o0, buf + o1, star_valid, lane, acc);
-      }
+    if (task.kind == 1)      sweep_off<T>(buf + o0, buf + o1, lane, acc);
+    else if (task.kind == 2) sweep_comp<T>(buf + o0, buf + o1, buf + o2, task.perm, lane, acc);
+    else if (task.kind == 3) {
+      if (star.slots == 3) sweep_star<T, 3>(buf + o0, buf + o1, star_valid, lane, acc);
+      else                 sweep_star<T, kRSlots>(buf + o0, buf + o1, star_valid, lane, acc);
     }
     if (SELF && nself > 0) sweep_self<T>(buf, srow, nself, lane, facc);
     __syncwarp();
@@ -512,15 +466,11 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    if constexpr (LIST) {
-      if (task.kind == 4) sweep_list<T>(stages, la, lb, task.g1, lane, acc);
-    } else {
-      if (task.kind == 1)      sweep_off<T>(stages + o0, stages + o1, lane, acc);
-      else if (task.kind == 2) sweep_comp<T>(stages + o0, stages + o1, stages + o2, task.perm, lane, acc);
-      else if (task.kind == 3) {
-        if (star.slots == 3) sweep_star<T, 3>(stages + o0, stages + o1, star_valid, lane, acc);
-        else                 sweep_star<T, kRSlots>(stages + o0, stages + o1, star_valid, lane, acc);
-      }
+    if (task.kind == 1)      sweep_off<T>(stages + o0, stages + o1, lane, acc);
+    else if (task.kind == 2) sweep_comp<T>(stages + o0, stages + o1, stages + o2, task.perm, lane, acc);
+    else if (task.kind == 3) {
+      if (star.slots == 3) sweep_star<T, 3>(stages + o0, stages + o1, star_valid, lane, acc);
+      else                 sweep_star<T, kRSlots>(stages + o0, stages + o1, star_valid, lane, acc);
     }
     if (SELF && nself > 0) sweep_self<T>(stages, srow, nself, lane, facc);
     pending = 1;
@@ -550,9 +500,6 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
       const int ri = g * kG + i, rj = g * kG + j;
       if (ri < n && rj < n) block[(size_t)ri * n + rj] = dacc;
     }
-  }
-  else if (task.kind == 4) {
-    if (lane < task.g1) { int i, j; unrank_pair(task.g0 + lane, n, i, j); block[(size_t)i * n + j] = dacc; }
   }
   else if (task.kind == 3) {
     const int r = task.g1 + lane;
@@ -644,9 +591,14 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
               }
             }
             __syncthreads();
+            asm volatile("" ::: "memory");      // the block loads below stay below the flag wait
             for (int e = threadIdx.x; e < len; e += kRThreads) {
-              double v = 0.;
-              for (int r = 0; r < tail.nranks; ++r) v += ld_volatile_f64(tail.peer_block[r] + e);
+              double part[BZ_MAX_PEERS];
+#pragma unroll
+              for (int r = 0; r < BZ_MAX_PEERS; ++r) part[r] = (r < tail.nranks) ? ld_relaxed_sys_f64(tail.peer_block[r] + e) : 0.;
+              double v = part[0];
+#pragma unroll
+              for (int r = 1; r < BZ_MAX_PEERS; ++r) v += part[r];      // rank order; + 0.0 past nranks is exact
               table[e] = v;
             }
             __syncthreads();
@@ -681,12 +633,12 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
 
 // ---- host side -------------------------------------------------------------------------------
 
-template <int T, int STAGES, bool SELF, bool CLUSTER, bool LIST = false>
+template <int T, int STAGES, bool SELF, bool CLUSTER>
 static int launch_ring_cfg(const RowTable& rows, const SelfList& self, RingTail& tail, const StarList& star, int n, int C, int64_t d,
                            double* parts, cudaStream_t st) {
   const int ng = (n + kG - 1) / kG;
   const size_t smem = (size_t)STAGES * ng * kG * T * sizeof(float) + 2 * STAGES * sizeof(unsigned long long);
-  auto kernel = k2_ring<T, STAGES, SELF, CLUSTER, LIST>;
+  auto kernel = k2_ring<T, STAGES, SELF, CLUSTER>;
   static unsigned long long opted = 0;
   static int max_clusters[64][kRMaxCluster + 1] = {};
   int dev = 0;
@@ -815,19 +767,11 @@ int launch_pairdist_ring(const RowTable& rows, int n, int64_t d, double* parts, 
       }
     }
   }
-  {
-    // small n: deal the pairs out evenly instead of 25-slot blocks (BYZAGG_K2_NOLIST=1: blocks, for A/B runs)
-    const char* nolist = getenv("BYZAGG_K2_NOLIST");
-    const int npairs = n * (n - 1) / 2, per = (npairs + kRWarps - 1) / kRWarps;
-    if (C == 1 && star.count == 0 && n >= 2 && per <= kListMax && n <= 20 && !(nolist && nolist[0] == '1')) star.list_k = per;
-  }
 #define BZ_RING(T, S, CL) (selfk ? launch_ring_cfg<T, S, true, CL>(rows, self, tail, star, n, C, d, parts, st) : launch_ring_cfg<T, S, false, CL>(rows, self, tail, star, n, C, d, parts, st))
   int nparts;
   if (C == 1) {
     if (rows_alloc > 25) return -1;
-    if (star.list_k > 0) nparts = selfk ? launch_ring_cfg<512, 4, true, false, true>(rows, self, tail, star, n, C, d, parts, st)
-                                        : launch_ring_cfg<512, 4, false, false, true>(rows, self, tail, star, n, C, d, parts, st);
-    else                 nparts = BZ_RING(512, 4, false);
+    nparts = BZ_RING(512, 4, false);
   } else if (rows_alloc <= 35) nparts = BZ_RING(512, 3, true);
   else                         nparts = BZ_RING(256, 3, true);   // (512-column tiles with 2 stages measured 20 % slower at n = 40...51)
 #undef BZ_RING
