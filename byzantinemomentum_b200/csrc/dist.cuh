@@ -13,7 +13,7 @@ namespace bz {
 // [kWsHeader, kWsHeader + n*n*8)       : reduced block (double[n*n] or double[n])
 // [.., + kMaxParts * n*n*8)            : per-CTA partial blocks of K2 / K2'
 constexpr size_t kWsHeader = 1024;
-constexpr int    kMaxParts = 304;     // >= number of CTAs K2 / K2' ever launch along x (2 per SM)
+constexpr int    kMaxParts = 336;     // >= number of CTAs K2 / K2' ever launch along x (2 per SM) + the group blocks of the fused reduction
 size_t workspace_bytes(int n);
 
 struct Workspace {

@@ -38,7 +38,10 @@
 namespace bz {
 
 constexpr int kG = 5;
-constexpr int kRWarps = 12;
+constexpr int kRWarps = 12;             // warps (= tasks) per CTA ...
+constexpr int kRWarpsSmall = 6;         // ... or 6, two CTAs per SM, when all tasks fit 6 warps (n <= 15): a warp's 25-slot
+                                        // task takes the same time per tile whatever n, so small n is bound by tiles per
+                                        // SM per unit time, and two resident CTAs walk two tile streams at once
 constexpr int kRThreads = kRWarps * 32;
 constexpr int kRSlots = kG * kG;
 constexpr size_t kRSmemBudget = 226 * 1024;
@@ -302,10 +305,10 @@ __device__ __forceinline__ void ring_flush(u64 (&acc)[kRSlots], int lane, double
 }
 
 // Cooperative staging of one (ragged) tile with cp.async, zero fill past d (rows 16-byte aligned).
-template <int T>
+template <int T, int THREADS>
 __device__ __forceinline__ void ring_stage_tail(float* buf, const RowTable& rows, int n, int64_t base, int64_t d) {
   constexpr int Q = T / 4;
-  for (int q = threadIdx.x; q < n * Q; q += kRThreads) {
+  for (int q = threadIdx.x; q < n * Q; q += THREADS) {
     const int r = q / Q, cq = q - r * Q;
     const float* row = rows.p[r];
     const int64_t col = base + (int64_t)cq * 4;
@@ -318,12 +321,13 @@ __device__ __forceinline__ void ring_stage_tail(float* buf, const RowTable& rows
 
 // One CTA = 12 warps = 12 tasks; a cluster of C CTAs covers tasks [0, 12 C) of the same tiles.
 // parts[cluster * n * n + i * n + j] (i < j; i == j for the rows of `self`).
-template <int T, int STAGES, bool SELF, bool CLUSTER>
-__global__ void __launch_bounds__(kRThreads, 1)
+template <int T, int STAGES, bool SELF, bool CLUSTER, int W>
+__global__ void __launch_bounds__(W * 32, W == kRWarps ? 1 : 2)
 k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList self, const __grid_constant__ RingTail tail,
         const __grid_constant__ StarList star, const int n, const int csize, const int64_t d, const int64_t nfull,
         double* __restrict__ parts) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int kThreads = W * 32;
   pdl_trigger();                     // K3 / K4 may be scheduled while this grid drains (they wait for its completion)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ng = (n + kG - 1) / kG;
@@ -339,16 +343,16 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
 
   Task task;
   if (star.count == 0) {
-    task = make_task(rank * kRWarps + warp, ng);
+    task = make_task(rank * W + warp, ng);
   } else {
     // reuse call: star task t = (new row t / chunks, rows [slots (t % chunks), + slots)); g1 = first ROW here
-    const int chunks = (n + star.slots - 1) / star.slots, t = rank * kRWarps + warp;
+    const int chunks = (n + star.slots - 1) / star.slots, t = rank * W + warp;
     task = Task{0, -1, -1, -1, 0};
     if (t < star.count * chunks) { task.kind = 3; task.g0 = star.row[t / chunks]; task.g1 = (t % chunks) * star.slots; }
   }
   // Rows this warp brings in: global issue slot q = r mod (12 C) -> CTA q mod C, warp q / C
   const int slot = warp * C + rank;
-  const int stride = kRWarps * C;
+  const int stride = W * C;
   const float* my_row[3];
   int my_idx[3];
   int nmine = 0;
@@ -364,7 +368,7 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
       mbar_init(&full[s], 1);            // ONE arrival (thread 0) carrying the expected bytes of the whole tile; the copies
                                          // are issued by the warps that own the rows, in this CTA and in its peers, and may
                                          // complete before that arrival (the transaction count is signed)
-      mbar_init(&empty[s], kRWarps * C);
+      mbar_init(&empty[s], W * C);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -411,10 +415,10 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
   int srow[kSelfPerWarp] = {0, 0, 0};
   int nself = 0;
   if (SELF) {
-    const int gw = rank * kRWarps + warp;     // entry e of the list belongs to warp e mod (12 C)
+    const int gw = rank * W + warp;     // entry e of the list belongs to warp e mod (12 C)
 #pragma unroll
     for (int q = 0; q < kSelfPerWarp; ++q)
-      if (gw + q * kRWarps * C < self.count) { srow[q] = self.row[gw + q * kRWarps * C]; nself = q + 1; }
+      if (gw + q * W * C < self.count) { srow[q] = self.row[gw + q * W * C]; nself = q + 1; }
   }
   // shared-memory offsets of the task's row groups (absent groups read group 0: discarded)
   const int o0 = task.kind == 3 ? task.g0 * T : (task.g0 >= 0 ? task.g0 : 0) * kG * T;
@@ -462,7 +466,7 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
   const int64_t ntiles = (d + T - 1) / T;
   if (ntiles > nfull && (nfull % nclusters) == cluster_id) {
     __syncthreads();                 // this CTA's ring is drained: every tile issued (here or by a peer) was awaited above
-    ring_stage_tail<T>(stages, rows, n, nfull * T, d);
+    ring_stage_tail<T, kThreads>(stages, rows, n, nfull * T, d);
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
@@ -538,7 +542,7 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
     __syncthreads();
     if (elected) {
       __threadfence();
-      for (int e = threadIdx.x; e < len; e += kRThreads) {
+      for (int e = threadIdx.x; e < len; e += kThreads) {
         double v[kTailGroup];
 #pragma unroll
         for (int p = 0; p < kTailGroup; ++p) v[p] = (p < members) ? __ldcg(parts + (size_t)(first + p) * len + e) : 0.;
@@ -557,7 +561,7 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
         if (tail.kind == 4) {
           // phase A of the d-sharded path: this rank's reduced block (entries outside i < j are 0)
           double* out_block = reinterpret_cast<double*>(tail.order);
-          for (int e = threadIdx.x; e < len; e += kRThreads) {
+          for (int e = threadIdx.x; e < len; e += kThreads) {
             double sum = 0.;
             for (int g = 0; g < ngroups; ++g) sum += __ldcg(gblocks + (size_t)g * len + e);
             out_block[e] = (e / n < e % n) ? sum : 0.;
@@ -571,7 +575,7 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
           if (tail.nranks > 0) {
             // ---- exchange over peer memory, inside this launch ----
             double* mine = tail.peer_block[tail.rank];
-            for (int e = threadIdx.x; e < len; e += kRThreads) {
+            for (int e = threadIdx.x; e < len; e += kThreads) {
               const int i = e / n, j = e - i * n;
               double v = 0.;
               if (i <= j)
@@ -592,7 +596,7 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
             }
             __syncthreads();
             asm volatile("" ::: "memory");      // the block loads below stay below the flag wait
-            for (int e = threadIdx.x; e < len; e += kRThreads) {
+            for (int e = threadIdx.x; e < len; e += kThreads) {
               double part[BZ_MAX_PEERS];
 #pragma unroll
               for (int r = 0; r < BZ_MAX_PEERS; ++r) part[r] = (r < tail.nranks) ? ld_relaxed_sys_f64(tail.peer_block[r] + e) : 0.;
@@ -603,7 +607,7 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
             }
             __syncthreads();
           } else
-          for (int e = threadIdx.x; e < len; e += kRThreads) {
+          for (int e = threadIdx.x; e < len; e += kThreads) {
             const int i = e / n, j = e - i * n;
             double v = 0.;
             if (i <= j) {
@@ -633,12 +637,12 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
 
 // ---- host side -------------------------------------------------------------------------------
 
-template <int T, int STAGES, bool SELF, bool CLUSTER>
+template <int T, int STAGES, bool SELF, bool CLUSTER, int W = kRWarps>
 static int launch_ring_cfg(const RowTable& rows, const SelfList& self, RingTail& tail, const StarList& star, int n, int C, int64_t d,
                            double* parts, cudaStream_t st) {
   const int ng = (n + kG - 1) / kG;
   const size_t smem = (size_t)STAGES * ng * kG * T * sizeof(float) + 2 * STAGES * sizeof(unsigned long long);
-  auto kernel = k2_ring<T, STAGES, SELF, CLUSTER>;
+  auto kernel = k2_ring<T, STAGES, SELF, CLUSTER, W>;
   static unsigned long long opted = 0;
   static int max_clusters[64][kRMaxCluster + 1] = {};
   int dev = 0;
@@ -650,11 +654,11 @@ static int launch_ring_cfg(const RowTable& rows, const SelfList& self, RingTail&
   }
   const int64_t nfull = d / T, ntiles = (d + T - 1) / T;
   cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(kRThreads);
+  cfg.blockDim = dim3(W * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
-  int nclusters = sm_count() / C;
+  int nclusters = sm_count() * (W == kRWarps ? 1 : 2) / C;
   if (CLUSTER) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)C;
@@ -706,7 +710,14 @@ int launch_pairdist_ring(const RowTable& rows, int n, int64_t d, double* parts, 
   int C = ring_cluster_size(n);
   if (C == 0) return -1;
   if (force_cluster > C && force_cluster <= kRMaxCluster) C = force_cluster;   // experiments: more CTAs per tile than needed
-  if (nself > kRWarps * C * kSelfPerWarp) return -1;
+  // warps per CTA: 6 (two CTAs per SM) when every task fits them (n <= 15), else 12 (BYZAGG_K2_W12=1: always 12, for A/B runs)
+  const auto warps_for = [](int rows_n, int c) {
+    const char* w12 = getenv("BYZAGG_K2_W12");
+    const int g = (rows_n + kG - 1) / kG;
+    return (c == 1 && ring_ntasks(g) <= kRWarpsSmall && rows_n <= 3 * kRWarpsSmall && !(w12 && w12[0] == '1')) ? kRWarpsSmall : kRWarps;
+  };
+  const int W = warps_for(n, C);
+  if (nself > W * C * kSelfPerWarp) return -1;
   for (int r = 0; r < n; ++r)
     if ((((uintptr_t)rows.p[r]) & 15) != 0) return -1;
   SelfList self;
@@ -752,10 +763,11 @@ int launch_pairdist_ring(const RowTable& rows, int n, int64_t d, double* parts, 
       const auto geometry = [](int alloc, int c) { return c == 1 ? 0 : alloc <= 35 ? 1 : 2; };
       // 3 rows per star task when the cluster has the warps for it, else 25
       int slots = 3;
-      if (nfresh * ((n + slots - 1) / slots) > kRWarps * C) slots = kRSlots;
+      if (nfresh * ((n + slots - 1) / slots) > W * C) slots = kRSlots;
       const int chunks = (n + slots - 1) / slots;
-      ok = ok && nfresh >= 1 && nfresh <= kStarMax && nfresh * chunks <= kRWarps * C && nfresh < n
-              && ring_cluster_size(select->u_old) == C && geometry(old_alloc, C) == geometry(rows_alloc, C);
+      ok = ok && nfresh >= 1 && nfresh <= kStarMax && nfresh * chunks <= W * C && nfresh < n
+              && ring_cluster_size(select->u_old) == C && geometry(old_alloc, C) == geometry(rows_alloc, C)
+              && warps_for(select->u_old, C) == W;
       if (ok) {
         star.count = nfresh;
         star.slots = slots;
@@ -771,7 +783,9 @@ int launch_pairdist_ring(const RowTable& rows, int n, int64_t d, double* parts, 
   int nparts;
   if (C == 1) {
     if (rows_alloc > 25) return -1;
-    nparts = BZ_RING(512, 4, false);
+    if (W == kRWarpsSmall) nparts = selfk ? launch_ring_cfg<512, 3, true, false, kRWarpsSmall>(rows, self, tail, star, n, C, d, parts, st)
+                                          : launch_ring_cfg<512, 3, false, false, kRWarpsSmall>(rows, self, tail, star, n, C, d, parts, st);
+    else                   nparts = BZ_RING(512, 4, false);
   } else if (rows_alloc <= 35) nparts = BZ_RING(512, 3, true);
   else                         nparts = BZ_RING(256, 3, true);   // (512-column tiles with 2 stages measured 20 % slower at n = 40...51)
 #undef BZ_RING

@@ -14,6 +14,7 @@ compiled library every entry point raises; there is no CPU fallback.
 
 import ctypes
 import math
+import time
 import weakref
 
 import torch
@@ -23,7 +24,7 @@ from . import _lib, hostmem
 __all__ = ["average", "median", "trmean", "phocas", "meamed", "krum", "bulyan", "brute", "aksel", "cge",
            "pairdist_partial", "rowdist_partial", "krum_select", "bulyan_select", "brute_select",
            "rowdist_select", "average_selected", "bulyan_reduce", "avg_dev_max_async", "compute_avg_dev_max",
-           "config", "Plan", "pair_cache_stats", "GradientStack"]
+           "config", "Plan", "pair_cache_stats", "GradientStack", "host_path_report"]
 
 class _Config:
   """ strict_status: after brute / bulyan, read the device status word (one 4-byte D2H copy,
@@ -44,7 +45,7 @@ config = _Config()
 # Argument plumbing
 
 class _Prepared:
-  __slots__ = ("rows", "n", "d", "device", "ptrs", "stream", "to_cpu", "keep")
+  __slots__ = ("rows", "n", "d", "device", "ptrs", "stream", "to_cpu", "keep", "host_mode", "host_t0")
 
 _workspaces = {}
 _staging = {}
@@ -69,6 +70,47 @@ _F32 = torch.float32
 
 _COPY_LANES = 4
 _copy_lanes = {}
+
+class _HostPath:
+  """ How host rows reach the GPU is decided by MEASUREMENT, per device: the right answer differs between
+  boxes of the same model (profiles/README.md: pinned rows on the far socket copy at 8.5 GB/s on one
+  stream and at 53 GB/s on four; on other boxes four streams are the slow ones).  Candidates:
+    "lanes"  the row copies spread over 4 streams,
+    "lane"   the row copies on the current stream,
+    "direct" no staging: the kernel reads the PINNED host rows in place over PCIe (unified addressing: a
+             pinned allocation is device accessible at its own address) — one pass over the data, for the
+             single-pass (coordinate-wise) rules only; each byte crosses PCIe exactly once either way.
+  The first calls try each candidate once (wall clock of the whole call: it ends with a synchronisation),
+  then the fastest is kept. """
+  def __init__(self):
+    self.times = {}
+    self.best = {}
+  def choose(self, single_pass, pinned):
+    key = (single_pass, pinned)
+    if key in self.best:
+      return self.best[key]
+    candidates = ["lanes", "lane"] + (["direct"] if single_pass and pinned else [])
+    seen = self.times.setdefault(key, {})
+    for mode in candidates:
+      if len(seen.get(mode, ())) < 2:          # two samples each: the first one pays one-time costs
+        return mode
+    self.best[key] = min(candidates, key=lambda mode: min(seen[mode]))
+    return self.best[key]
+  def record(self, single_pass, pinned, mode, seconds):
+    key = (single_pass, pinned)
+    if key not in self.best:
+      self.times.setdefault(key, {}).setdefault(mode, []).append(seconds)
+
+_host_paths = {}
+
+def host_path_report(device_index=None):
+  """ What the measurement found (bench / tests): {(single_pass, pinned): {"best": mode, "ms": {mode: best ms}}}. """
+  if device_index is None:
+    device_index = torch.cuda.current_device()
+  hp = _host_paths.get(device_index)
+  if hp is None:
+    return {}
+  return {f"single_pass={k[0]},pinned={k[1]}": dict(best=hp.best.get(k), ms={m: round(min(v) * 1e3, 3) for m, v in t.items() if v}) for k, t in hp.times.items()}
 
 def _copy_streams(device):
   lanes = _copy_lanes.get(device.index)
@@ -131,7 +173,7 @@ class _CallCache:
 
 _call_cache = _CallCache()
 
-def _prepare(gradients):
+def _prepare(gradients, single_pass=False):
   prep = _call_cache.lookup(gradients)
   if prep is not None:
     prep.stream = torch.cuda.current_stream(prep.device).cuda_stream
@@ -141,6 +183,7 @@ def _prepare(gradients):
     raise _lib.LibraryError("no CUDA device available: byzantinemomentum_b200 runs on B200 GPUs only (no CPU fallback)")
   _lib.lib()
   prep = _Prepared()
+  prep.host_mode = None
   n, d = len(gradients), first.shape[0]
   keep = None
   if first.device.type == "cuda":
@@ -153,6 +196,22 @@ def _prepare(gradients):
     uniq = {}
     for g in gradients:
       uniq.setdefault(id(g), g)
+    pinned = contiguous and all(g.is_pinned() for g in uniq.values())
+    path = _host_paths.get(device.index)
+    if path is None:
+      path = _host_paths[device.index] = _HostPath()
+    mode = path.choose(single_pass, pinned)
+    prep.host_mode = (single_pass, pinned, mode)
+    torch.cuda.current_stream(device).synchronize()        # the clock below times this call only
+    prep.host_t0 = time.perf_counter()
+    if mode == "direct":
+      rows = gradients
+      prep.to_cpu = True
+      addresses = tuple([g.data_ptr() for g in rows])
+      prep.rows, prep.n, prep.d, prep.device, prep.keep = rows, n, d, device, None
+      prep.ptrs = (ctypes.c_void_p * n)(*addresses)
+      prep.stream = torch.cuda.current_stream(device).cuda_stream
+      return prep
     key = (device.index, len(uniq), d)
     buf = _staging.get(key)
     if buf is None:
@@ -165,17 +224,19 @@ def _prepare(gradients):
     # 53 GB/s on two or more — with one stream the e2e step took 12.5 ms, 2.5x the box's own PCIe
     # floor, and varied 4x between boxes depending on where the caller's pages happened to be.
     current = torch.cuda.current_stream(device)
-    lanes = _copy_streams(device)
-    for lane in lanes:
-      lane.wait_stream(current)          # the previous call's kernels have finished with the staging buffer
+    lanes = _copy_streams(device) if mode == "lanes" else [current]
+    if mode == "lanes":
+      for lane in lanes:
+        lane.wait_stream(current)        # the previous call's kernels have finished with the staging buffer
     slot = {}
     for k, (ident, g) in enumerate(uniq.items()):
       row = buf[k, :d]
       with torch.cuda.stream(lanes[k % len(lanes)]):
         row.copy_(g, non_blocking=True)
       slot[ident] = row
-    for lane in lanes:
-      current.wait_stream(lane)
+    if mode == "lanes":
+      for lane in lanes:
+        current.wait_stream(lane)
     rows = [slot[id(g)] for g in gradients]
     keep = buf
     prep.to_cpu = True
@@ -221,6 +282,9 @@ def _finish(prep, out):
     _host_out[key] = pinned
   pinned.copy_(out, non_blocking=True)
   torch.cuda.current_stream(prep.device).synchronize()
+  if prep.host_mode is not None:
+    single_pass, was_pinned, mode = prep.host_mode
+    _host_paths[prep.device.index].record(single_pass, was_pinned, mode, time.perf_counter() - prep.host_t0)
   return pinned.clone()
 
 def _raise_status(code):
@@ -233,7 +297,7 @@ def _raise_status(code):
 # Coordinate-wise rules
 
 def _coordinate(name, gradients, f=None):
-  prep = _prepare(gradients)
+  prep = _prepare(gradients, single_pass=True)
   out = torch.empty(prep.d, dtype=torch.float32, device=prep.device)
   fn = getattr(_lib.lib(), "bz_" + name)
   with _on(prep.device):

@@ -1,11 +1,13 @@
 set -x
 mkdir -p gpurun_out
-( timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/p2p_check.py 2>&1 | tail -8 ) > gpurun_out/r2_p2p_n2b.log 2>&1
-( timeout 300 python tools/k2_ab.py --cases 11:1310922,16:1310922,20:1310922,11:36489290,5:1310922,2:1310922 --no-alias --json gpurun_out/k2_ab_list.json 2>&1 | tail -8 ) > gpurun_out/r2_k2ab_list.log 2>&1
-( timeout 600 python -m pytest tests/test_cuda_abi.py tests/test_cuda_golden.py tests/test_cuda_reuse.py -q -m gpu -x 2>&1 | tail -5 ) > gpurun_out/r2_t12.log 2>&1
-( timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 50 --warmup 5 --no-sweep 2>gpurun_out/r2_bench_n2.err | tail -1 ) > gpurun_out/r2_bench_n2b.json
-cat gpurun_out/r2_p2p_n2b.log gpurun_out/r2_k2ab_list.log; tail -4 gpurun_out/r2_t12.log; tail -3 gpurun_out/r2_bench_n2.err; python -c "
+( timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -8 ) > gpurun_out/r2_t13.log 2>&1
+( timeout 900 python bench.py --steps 200 --warmup 10 2> gpurun_out/r2_bench2.err | tail -1 ) > gpurun_out/r2_bench2.json
+( timeout 300 python bench.py --impl reference --steps 5 --warmup 1 2>> gpurun_out/r2_bench2.err | tail -1 ) > gpurun_out/r2_bench2_ref.json
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 40 --csv --log-file gpurun_out/r2_bench_launches.csv python bench.py --steps 5 --warmup 3 --no-sweep > gpurun_out/ncu4.log 2>&1
+tail -4 gpurun_out/r2_t13.log; tail -3 gpurun_out/r2_bench2.err; python - <<'PY'
 import json
-l=json.loads(open('gpurun_out/r2_bench_n2b.json').read())
-for r in l['sharded']['collective']['rules']: print(r)
-print(l['e2e'])"
+l=json.loads(open('gpurun_out/r2_bench2.json').read())
+print({k:l[k] for k in ('value','ms_per_step','gpu_launches','clocks')}); print(l['roofline']); print(l['e2e']); print(l['cpu_baseline']); print(l['config'])
+r=json.loads(open('gpurun_out/r2_bench2_ref.json').read()); print(r['value'], r['ms_per_step'], r['cpu_baseline'], r['config']==l['config'])
+for row in l.get('sweep',[])[:12]: print({k:(round(v,4) if isinstance(v,float) else v) for k,v in row.items()})
+PY
