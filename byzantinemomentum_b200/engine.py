@@ -76,12 +76,11 @@ class _HostPath:
   boxes of the same model (profiles/README.md: pinned rows on the far socket copy at 8.5 GB/s on one
   stream and at 53 GB/s on four; on other boxes four streams are the slow ones).  Candidates:
     "lanes"  the row copies spread over 4 streams,
-    "lane"   the row copies on the current stream,
-    "direct" no staging: the kernel reads the PINNED host rows in place over PCIe (unified addressing: a
-             pinned allocation is device accessible at its own address) — one pass over the data, for the
-             single-pass (coordinate-wise) rules only; each byte crosses PCIe exactly once either way.
-  The first calls try each candidate once (wall clock of the whole call: it ends with a synchronisation),
-  then the fastest is kept. """
+    "lane"   the row copies on the current stream.
+  (A third one — no staging, the kernel reading the pinned rows in place over PCIe — measured the same
+  2.7 ms as the copies and needs `Tensor.is_pinned()`, which costs ~1 ms PER TENSOR on some boxes: dropped.)
+  The first calls try each candidate twice (wall clock of the whole call: it ends with a
+  synchronisation), then the fastest is kept. """
   def __init__(self):
     self.times = {}
     self.best = {}
@@ -89,7 +88,7 @@ class _HostPath:
     key = (single_pass, pinned)
     if key in self.best:
       return self.best[key]
-    candidates = ["lanes", "lane"] + (["direct"] if single_pass and pinned else [])
+    candidates = ["lanes", "lane"]
     seen = self.times.setdefault(key, {})
     for mode in candidates:
       if len(seen.get(mode, ())) < 2:          # two samples each: the first one pays one-time costs
@@ -196,7 +195,7 @@ def _prepare(gradients, single_pass=False):
     uniq = {}
     for g in gradients:
       uniq.setdefault(id(g), g)
-    pinned = contiguous and all(g.is_pinned() for g in uniq.values())
+    pinned = False          # never asked: Tensor.is_pinned() is a slow driver query on some boxes
     path = _host_paths.get(device.index)
     if path is None:
       path = _host_paths[device.index] = _HostPath()
@@ -204,14 +203,6 @@ def _prepare(gradients, single_pass=False):
     prep.host_mode = (single_pass, pinned, mode)
     torch.cuda.current_stream(device).synchronize()        # the clock below times this call only
     prep.host_t0 = time.perf_counter()
-    if mode == "direct":
-      rows = gradients
-      prep.to_cpu = True
-      addresses = tuple([g.data_ptr() for g in rows])
-      prep.rows, prep.n, prep.d, prep.device, prep.keep = rows, n, d, device, None
-      prep.ptrs = (ctypes.c_void_p * n)(*addresses)
-      prep.stream = torch.cuda.current_stream(device).cuda_stream
-      return prep
     key = (device.index, len(uniq), d)
     buf = _staging.get(key)
     if buf is None:
@@ -273,19 +264,16 @@ def _finish(prep, out):
   through a cached pinned buffer so that the D2H transfer runs at full PCIe rate). """
   if not prep.to_cpu:
     return out
-  key = (prep.device.index, prep.d)
-  pinned = _host_out.get(key)
-  if pinned is None:
-    _host_out.clear()
-    with hostmem.gpu_local_cpus(prep.device.index):         # pages on the GPU's NUMA node
-      pinned = torch.empty(prep.d, dtype=torch.float32, pin_memory=True)
-    _host_out[key] = pinned
-  pinned.copy_(out, non_blocking=True)
+  # The result goes straight into a NEW pinned tensor, which the caller owns: PyTorch's caching host
+  # allocator recycles such blocks, so after the first steps this costs neither a cudaHostAlloc nor page
+  # faults — the former `cached pinned buffer + clone()` paid a fresh 5 MB of page faults per call.
+  result = torch.empty(prep.d, dtype=torch.float32, pin_memory=True)
+  result.copy_(out, non_blocking=True)
   torch.cuda.current_stream(prep.device).synchronize()
   if prep.host_mode is not None:
     single_pass, was_pinned, mode = prep.host_mode
     _host_paths[prep.device.index].record(single_pass, was_pinned, mode, time.perf_counter() - prep.host_t0)
-  return pinned.clone()
+  return result
 
 def _raise_status(code):
   if code == _lib.STATUS_NO_FINITE_SET:
