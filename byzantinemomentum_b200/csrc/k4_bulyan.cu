@@ -163,7 +163,10 @@ bool launch_bulyan_reduce_static(const RowTable& rows, int n, int f, int m, cons
                                  const Geom& g, float* out, cudaStream_t st) {
   if (m != n - f - 2) return false;
 #define Y(N, F) if (n == N && f == F) { launch_static<N, F>(rows, g, order, status, out, st); return true; }
+  // the reference's grids (reproduce.py:109-209, reproduce-appendix.py: n = 11 / 25 / 51) and the
+  // tightest configuration n = 4f + 3 of every f (bulyan.py:104-105)
   Y(11, 2) Y(25, 5) Y(51, 12)
+  Y(7, 1) Y(15, 3) Y(19, 4) Y(23, 5) Y(27, 6) Y(31, 7) Y(35, 8) Y(39, 9) Y(43, 10) Y(47, 11)
 #undef Y
   return false;
 }

@@ -256,3 +256,18 @@ def test_cpu_tensors_are_staged():
   out = bz.gars["krum"](gradients=rows, f=f)
   parity.assert_bit_exact(out.numpy(), orc.krum(host, f), "krum staged")
   assert bz.gars["krum"].influence(rows[:n - 2], rows[n - 2:], f=f) == orc.influence("krum", host[:n - 2], host[n - 2:], f=f)
+
+@pytest.mark.parametrize("n,f", [(7, 1), (15, 3), (19, 4), (23, 5), (27, 6), (31, 7), (35, 8), (39, 9), (43, 10), (47, 11)])
+def test_bulyan_register_resident_reduce_for_every_tight_configuration(n, f):
+  """ n = 4f + 3 (the tightest n bulyan.py:104-105 accepts for each f) has a compile-time
+  `k4_bulyan_static<N, F, VEC>`; unaligned shard views take its VEC = 1 form. """
+  import byzantinemomentum_b200 as bz
+  d = 6007
+  rows, host = _distance_inputs(n, f, d, 7000 + n, "empire")
+  ref, info = orc.bulyan(host, f, return_info=True)
+  got = bz.gars["bulyan"](gradients=rows, f=f).cpu().numpy()
+  parity.assert_close_scaled(got, ref, parity.column_scale(info["stage1"]), f"bulyan n={n} f={f}", exempt=info["ambiguous"])
+  views = [r[1:] for r in rows[:n - f]] + [rows[-1][1:]] * f          # 4-byte aligned only
+  ref_v, info_v = orc.bulyan([h[1:] for h in host], f, return_info=True)
+  got_v = bz.gars["bulyan"](gradients=views, f=f).cpu().numpy()
+  parity.assert_close_scaled(got_v, ref_v, parity.column_scale(info_v["stage1"]), f"bulyan n={n} f={f} (views)", exempt=info_v["ambiguous"])

@@ -1,9 +1,11 @@
 set -x
 mkdir -p gpurun_out
-( timeout 300 python tools/e2e_parts.py 2>&1 | tail -12 ) > gpurun_out/r2_e2e_parts.log 2>&1
-( timeout 600 python bench.py --steps 200 --warmup 10 --no-sweep 2> gpurun_out/r2_bench4.err | tail -1 ) > gpurun_out/r2_bench4.json
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 125 -c 30 --csv --log-file gpurun_out/r2_bench_launches.csv python bench.py --steps 5 --warmup 3 --no-sweep > gpurun_out/ncu4.log 2>&1
-cat gpurun_out/r2_e2e_parts.log; tail -3 gpurun_out/r2_bench4.err; python -c "
+( timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 tools/p2p_check.py 2>&1 | tail -8 ) > gpurun_out/r2_p2p_n8.log 2>&1
+( timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 100 --warmup 5 2>gpurun_out/r2_bench_n8.err | tail -1 ) > gpurun_out/r2_bench_n8.json
+( timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus 8 --steps 3 --warmup 1 2>>gpurun_out/r2_bench_n8.err | tail -1 ) > gpurun_out/r2_bench_n8_ref.json
+cat gpurun_out/r2_p2p_n8.log; tail -3 gpurun_out/r2_bench_n8.err; python -c "
 import json
-l=json.loads(open('gpurun_out/r2_bench4.json').read())
-print(l['value'], l['ms_per_step'], l['roofline']['frac']); print(json.dumps(l['e2e'],indent=1))"
+l=json.loads(open('gpurun_out/r2_bench_n8.json').read())
+print(l['value'], l['ms_per_step'], l['n_gpus'], l['clocks'])
+print(json.dumps(l['sharded'],indent=1)[:5000]); print(l['e2e'])
+print(open('gpurun_out/r2_bench_n8_ref.json').read()[:300])"
