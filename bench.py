@@ -293,7 +293,7 @@ def sharded_block(torch, dist, bz, sharded, device, world, rank, peak):
     rec = dict(gar=gar, n=n, f=f, d_per_gpu=d, steps=steps)
     local = [bz.Plan(gar, st, f=f) for st in stacks]
     rec["single_gpu_us"] = timed_max_over_ranks(torch, dist, device, lambda k: local[k % sets](), steps)
-    for exchange in ("nccl", "p2p", "fused"):
+    for exchange in (("nccl", "p2p", "fused") if world > 1 else ("nccl",)):
       try:
         plans = [sharded.ShardedPlan(gar, st, f=f, exchange=exchange) for st in stacks]
         rec[exchange + "_us"] = timed_max_over_ranks(torch, dist, device, lambda k: plans[k % sets](), steps)
@@ -512,7 +512,7 @@ def run_b200(args):
       line["torch_cuda_baseline"] = dict(error=str(err)[:200])
     if not args.no_sweep:
       line["sweep"] = sweep(torch, bz, device, peak)
-  if not args.no_sharded and (world > 1 or args.sharded):
+  if not args.no_sharded:
     try:
       line["sharded"] = sharded_block(torch, dist, bz, sharded, device, world, rank, peak)
     except Exception as err:
@@ -607,8 +607,7 @@ def main():
   ap.add_argument("--nb-byz", dest="f", type=int, default=10)
   ap.add_argument("--dim", dest="d", type=int, default=1_310_922)
   ap.add_argument("--no-sweep", action="store_true")
-  ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the `sharded` block (collective path + C4 strong scaling)")
-  ap.add_argument("--sharded", action="store_true", help="N = 1: also run the `sharded` block (its N = 1 reference line)")
+  ap.add_argument("--no-sharded", action="store_true", help="skip the `sharded` block (collective path at C3 per GPU + C4 strong scaling; at N = 1 it is the reference line of the series)")
   ap.add_argument("--exchange", choices=("auto", "nccl", "p2p"), default="auto",
                   help="N > 1, distance-based rules: all-gather (NCCL) or blocks read in place over NVLink peer memory")
   args = ap.parse_args()
