@@ -114,7 +114,6 @@ struct StarList {
   unsigned char row[kStarMax];
   int count;                // 0: the ordinary pass over all pairs
   int slots;                // rows per star task: 3 or 25
-  int pair;                 // two tiles per loop iteration (see the main loop)
 };
 
 // ---- cluster helpers -------------------------------------------------------------------------
@@ -329,7 +328,9 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
         double* __restrict__ parts) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int kThreads = W * 32;
-  pdl_trigger();                     // K3 / K4 may be scheduled while this grid drains (they wait for its completion)
+  // (No early `pdl_trigger()` here: A/B on one box, krum n = 25: 71.0 us with it, 65.9 without, 1394 vs 1296 us at
+  // d = 36.5M — the reduce pass's CTAs scheduled on the SMs that finish first only get in the way.  K3 / K4 are still
+  // launched with the programmatic attribute: they start when the last CTA of this grid exits.)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ng = (n + kG - 1) / kG;
   const int rows_alloc = ng * kG;
@@ -433,55 +434,36 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
   int pending = 0;
   int s = 0, sp = 0;
   unsigned parity = 0, pp = 0;
-  // Tiles per loop iteration: 1 (refill deferred by one iteration), or — `star.pair`, 4-stage rings only —
-  // 2: two tiles are swept back to back (8 steps of straight FP2 work) before the barrier / flush / refill
-  // bookkeeping, which then runs half as often; the refill of the two stages cannot be deferred (they are
-  // needed two iterations later), so it waits for the whole CTA to release them.
-  const int tpi = (STAGES == 4 && star.pair) ? 2 : 1;
-  for (int k = 0; k < mine; k += tpi) {
-    const int cnt = min(tpi, mine - k);
-    for (int t = 0; t < cnt; ++t) {
-      mbar_wait(&full[s + t], parity);
-      const float* buf = stages + (size_t)(s + t) * stage_floats;
-      if (task.kind == 1)      sweep_off<T>(buf + o0, buf + o1, lane, acc);
-      else if (task.kind == 2) sweep_comp<T>(buf + o0, buf + o1, buf + o2, task.perm, lane, acc);
-      else if (task.kind == 3) {
-        if (star.slots == 3) sweep_star<T, 3>(buf + o0, buf + o1, star_valid, lane, acc);
-        else                 sweep_star<T, kRSlots>(buf + o0, buf + o1, star_valid, lane, acc);
-      }
-      if (SELF && nself > 0) sweep_self<T>(buf, srow, nself, lane, facc);
+  // (Two tiles per loop iteration with a blocking refill — half the bookkeeping — was measured SLOWER:
+  // 62 vs 52 us at n = 25, d = 1.31M: every iteration then waits for the slowest warp of the CTA.)
+  for (int k = 0; k < mine; ++k) {
+    mbar_wait(&full[s], parity);
+    const float* buf = stages + (size_t)s * stage_floats;
+    if (task.kind == 1)      sweep_off<T>(buf + o0, buf + o1, lane, acc);
+    else if (task.kind == 2) sweep_comp<T>(buf + o0, buf + o1, buf + o2, task.perm, lane, acc);
+    else if (task.kind == 3) {
+      if (star.slots == 3) sweep_star<T, 3>(buf + o0, buf + o1, star_valid, lane, acc);
+      else                 sweep_star<T, kRSlots>(buf + o0, buf + o1, star_valid, lane, acc);
     }
+    if (SELF && nself > 0) sweep_self<T>(buf, srow, nself, lane, facc);
     __syncwarp();
     if (lane == 0) {
       // the values read from the stage have been consumed by the arithmetic above: a plain
       // (relaxed) arrive is enough to hand the stage back; `.release.cluster` here compiled to
       // MEMBAR + ERRBAR per arrive and took 37 % of the stall samples at n = 51
-      for (int t = 0; t < cnt; ++t) {
-        if (!CLUSTER) mbar_arrive(&empty[s + t]);
-        else
-          for (int r = 0; r < C; ++r) mbar_arrive_remote(&empty[s + t], (unsigned)r);
-      }
+      if (!CLUSTER) mbar_arrive(&empty[s]);
+      else
+        for (int r = 0; r < C; ++r) mbar_arrive_remote(&empty[s], (unsigned)r);
     }
-    if (task.kind != 0 && (pending += cnt) >= kFlushTiles) { pending = 0; ring_flush(acc, lane, dacc); }
-    if (tpi == 1) {
-      // refill the stage released one iteration ago (every warp of the cluster is past it by now)
-      if (refiller && k >= 1 && issued < mine) {
-        mbar_wait(&empty[sp], pp);
-        refill(sp);
-        ++issued;
-      }
-      sp = s; pp = parity;
-      if (++s == STAGES) { s = 0; parity ^= 1u; }
-    } else {
-      if (refiller)
-        for (int t = 0; t < cnt && issued < mine; ++t) {
-          mbar_wait(&empty[s + t], parity);
-          refill(s + t);
-          ++issued;
-        }
-      s += 2;
-      if (s == STAGES) { s = 0; parity ^= 1u; }
+    if (task.kind != 0 && ++pending == kFlushTiles) { pending = 0; ring_flush(acc, lane, dacc); }
+    // refill the stage released one iteration ago (every warp of the cluster is past it by now)
+    if (refiller && k >= 1 && issued < mine) {
+      mbar_wait(&empty[sp], pp);
+      refill(sp);
+      ++issued;
     }
+    sp = s; pp = parity;
+    if (++s == STAGES) { s = 0; parity ^= 1u; }
   }
   // Ragged tail tile (d not a multiple of T): cooperative staging with zero fill; every CTA of the
   // owning cluster stages it for itself (its own tasks)
@@ -800,10 +782,6 @@ int launch_pairdist_ring(const RowTable& rows, int n, int64_t d, double* parts, 
         for (int k = 0; k < kMaxN; ++k) tail.old_index[k] = -1;
       }
     }
-  }
-  {
-    const char* pair = getenv("BYZAGG_K2_PAIR");
-    star.pair = (pair && pair[0] == '1') ? 1 : 0;
   }
 #define BZ_RING(T, S, CL) (selfk ? launch_ring_cfg<T, S, true, CL>(rows, self, tail, star, n, C, d, parts, st) : launch_ring_cfg<T, S, false, CL>(rows, self, tail, star, n, C, d, parts, st))
   int nparts;

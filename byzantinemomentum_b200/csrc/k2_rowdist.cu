@@ -27,7 +27,6 @@ __global__ void __launch_bounds__(kRdThreads, 2)
 k2_rowdist(const __grid_constant__ RowTable rows, const int n, const float* __restrict__ center, const Geom g,
            double* __restrict__ parts, int32_t* __restrict__ order, unsigned* __restrict__ ticket, const int sqrt_norm) {
   __shared__ double warp_tot[kRdWarps][kMaxN];
-  pdl_trigger();                     // the K3 pass may be scheduled while this grid drains
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float acc[kMaxN];
 #pragma unroll

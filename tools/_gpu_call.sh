@@ -1,11 +1,8 @@
 set -x
 mkdir -p gpurun_out
-( timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 tools/p2p_check.py 2>&1 | tail -8 ) > gpurun_out/r2_p2p_n8.log 2>&1
-( timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 100 --warmup 5 2>gpurun_out/r2_bench_n8.err | tail -1 ) > gpurun_out/r2_bench_n8.json
-( timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus 8 --steps 3 --warmup 1 2>>gpurun_out/r2_bench_n8.err | tail -1 ) > gpurun_out/r2_bench_n8_ref.json
-cat gpurun_out/r2_p2p_n8.log; tail -3 gpurun_out/r2_bench_n8.err; python -c "
-import json
-l=json.loads(open('gpurun_out/r2_bench_n8.json').read())
-print(l['value'], l['ms_per_step'], l['n_gpus'], l['clocks'])
-print(json.dumps(l['sharded'],indent=1)[:5000]); print(l['e2e'])
-print(open('gpurun_out/r2_bench_n8_ref.json').read()[:300])"
+L=byzantinemomentum_b200
+( timeout 600 python tools/abbench.py --dist $L/libbyzagg.so $L/libbyzagg-notrig.so 2>&1 | tail -8 ) > gpurun_out/r2_ab_trigger.log 2>&1
+( timeout 200 python tools/k2_ab.py --cases 25:1310922,25:36489290 --no-alias --only ring 2>&1 | tail -3 ) > gpurun_out/r2_k2_now.log 2>&1
+( BYZAGG_LIBRARY=$PWD/$L/libbyzagg-notrig.so timeout 200 python tools/k2_ab.py --cases 25:1310922,25:36489290 --no-alias --only ring 2>&1 | tail -3 ) > gpurun_out/r2_k2_notrig.log 2>&1
+nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > gpurun_out/r2_clocks.txt
+cat gpurun_out/r2_ab_trigger.log gpurun_out/r2_k2_now.log gpurun_out/r2_k2_notrig.log gpurun_out/r2_clocks.txt
