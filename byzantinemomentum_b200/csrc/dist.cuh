@@ -72,7 +72,7 @@ int launch_pairdist_auto(const RowTable& rows, int u, int64_t d, double* parts, 
 // (sqrt_norm as in bz_rowdist_select) — the selection step without its launch; `ticket`: one zeroed word.
 int launch_rowdist(const RowTable& rows, int n, const float* const* host_rows, const float* center, int64_t d,
                    double* parts, cudaStream_t st, int reverse = 0, int32_t* order = nullptr, unsigned* ticket = nullptr,
-                   int sqrt_norm = 0);
+                   int sqrt_norm = 0, int dot = 0);
 
 // ---- K6: study metrics in one pass (k6_study.cu) -------------------------------------------------
 // avg = (rows[0] + rows[1] + ...)/n; stats[0] = sum avg^2, stats[1] = max |avg|,

@@ -22,7 +22,9 @@ constexpr int kRdWarps = kRdThreads / 32;
 constexpr int kRdChunk = 4;      // rows loaded together (4 x VEC values in flight per thread)
 constexpr int kRdFlush = 8;      // vectors between two flushes
 
-template <bool CENTER, int VEC>
+// DOT: sum_k x_r[k] * c[k] instead of the squared distance (the dot products of the study step,
+// attack.py:854-866: one vector against up to 64 others in one pass).
+template <bool CENTER, int VEC, bool DOT = false>
 __global__ void __launch_bounds__(kRdThreads, 2)
 k2_rowdist(const __grid_constant__ RowTable rows, const int n, const float* __restrict__ center, const Geom g,
            double* __restrict__ parts, int32_t* __restrict__ order, unsigned* __restrict__ ticket, const int sqrt_norm) {
@@ -66,14 +68,16 @@ k2_rowdist(const __grid_constant__ RowTable rows, const int n, const float* __re
               const int64_t e = e0 + q;
               const bool ok = live && e >= 0 && e < g.d;
               // out-of-range lanes must add exactly 0: take the centre itself
-              x[u][q] = ok ? __ldcs(rows.p[r0 + u] + e) : (CENTER ? c[q] : 0.f);
+              x[u][q] = ok ? __ldcs(rows.p[r0 + u] + e) : ((CENTER && !DOT) ? c[q] : 0.f);
             }
         }
 #pragma unroll
         for (int u = 0; u < kRdChunk; ++u)
 #pragma unroll
           for (int q = 0; q < VEC; ++q) {
-            if (CENTER) {
+            if (DOT) {
+              acc[r0 + u] = fmaf(x[u][q], c[q], acc[r0 + u]);
+            } else if (CENTER) {
               const float df = __fsub_rn(x[u][q], c[q]);
               acc[r0 + u] = __fadd_rn(acc[r0 + u], __fmul_rn(df, df));
             } else {
@@ -151,7 +155,7 @@ k2_rowdist(const __grid_constant__ RowTable rows, const int n, const float* __re
 
 
 int launch_rowdist(const RowTable& rows, int n, const float* const* host_rows, const float* center, int64_t d,
-                   double* parts, cudaStream_t st, int reverse, int32_t* order, unsigned* ticket, int sqrt_norm) {
+                   double* parts, cudaStream_t st, int reverse, int32_t* order, unsigned* ticket, int sqrt_norm, int dot) {
   // The centre doubles as the alignment reference ("out") of the geometry
   Geom g = make_geom(host_rows, n, center ? (const void*)center : (const void*)host_rows[0], nullptr, d, 4);
   g.reverse = reverse;
@@ -160,6 +164,11 @@ int launch_rowdist(const RowTable& rows, int n, const float* const* host_rows, c
   if (grid > cap) grid = cap;
   if (grid > kMaxParts) grid = kMaxParts;
   if (grid < 1) grid = 1;
+  if (dot && center != nullptr) {
+    if (g.vec == 4) k2_rowdist<true, 4, true><<<(unsigned)grid, kRdThreads, 0, st>>>(rows, n, center, g, parts, nullptr, nullptr, 0);
+    else            k2_rowdist<true, 1, true><<<(unsigned)grid, kRdThreads, 0, st>>>(rows, n, center, g, parts, nullptr, nullptr, 0);
+    return (int)grid;
+  }
   if (order != nullptr) cudaMemsetAsync(ticket, 0, sizeof(unsigned), st);
   if (g.vec == 4) {
     if (center) k2_rowdist<true, 4><<<(unsigned)grid, kRdThreads, 0, st>>>(rows, n, center, g, parts, order, ticket, sqrt_norm);

@@ -23,7 +23,7 @@ from . import _lib, hostmem
 
 __all__ = ["average", "median", "trmean", "phocas", "meamed", "krum", "bulyan", "brute", "aksel", "cge",
            "pairdist_partial", "rowdist_partial", "krum_select", "bulyan_select", "brute_select",
-           "rowdist_select", "average_selected", "bulyan_reduce", "avg_dev_max_async", "compute_avg_dev_max",
+           "rowdist_select", "average_selected", "bulyan_reduce", "avg_dev_max_async", "compute_avg_dev_max", "rowdots_async", "study_step",
            "config", "Plan", "pair_cache_stats", "GradientStack", "host_path_report"]
 
 class _Config:
@@ -544,7 +544,9 @@ def compute_avg_dev_max(samples):
 
 def _compute_avg_dev_max(samples, n):
   avg, stats = avg_dev_max_async(samples)
-  host = stats.tolist()                                       # the only synchronisation
+  return _study_tuple(avg, stats.tolist(), n)                 # the only synchronisation
+
+def _study_tuple(avg, host, n):
   norm_avg = ctypes.c_float(math.sqrt(host[0])).value      # :110 returns an fp32 norm: same rounding in the logs
   norm_max = host[1]
   if n >= 2:
@@ -555,6 +557,90 @@ def _compute_avg_dev_max(samples, n):
   else:
     norm_dev = math.nan                                       # :122-123
   return avg, norm_avg, norm_dev, norm_max
+
+def rowdots_async(center, rows):
+  """ DEVICE fp64 vector: out[i] = <rows[i], center>, all rows in one pass (`bz_rowdots`).  No sync. """
+  rows = list(rows)
+  if len(rows) > _lib.MAX_N:
+    return torch.cat([rowdots_async(center, rows[k:k + _lib.MAX_N]) for k in range(0, len(rows), _lib.MAX_N)])
+  prep = _prepare_device(rows, "the study dot products take CUDA tensors")
+  if center.dtype != torch.float32 or center.shape != (prep.d,) or center.device != prep.device or not center.is_contiguous():
+    raise ValueError("center must be a contiguous float32 vector like the rows")
+  out = torch.empty(prep.n, dtype=torch.float64, device=prep.device)
+  ws = _workspace(prep.device, prep.stream)
+  with _on(prep.device):
+    code = _lib.lib().bz_rowdots(prep.ptrs, prep.n, center.data_ptr(), prep.d, out.data_ptr(), ws.data_ptr(), ws.numel(), prep.stream)
+  _lib.check(code, "bz_rowdots")
+  return out
+
+def study_step(grad_sampleds, grad_honests, grad_attacks, grad_defense, pasts, momentum):
+  """ Everything attack.py:846-866 computes for one line of the study file, on the device:
+    * the three `tools.compute_avg_dev_max` calls (K6, one pass each; a repeated list is computed once),
+    * the norm and the largest |coordinate| of the defense gradient,
+    * the six cosines between the sampled / honest / attack averages and the defense gradient,
+    * the cosine with the last past gradient and the curvature sum over all past gradients
+  with THREE passes of `bz_rowdots` (one vector against many) instead of 7 + len(pasts) `torch.dot(...).item()`
+  and ONE device->host read for the whole step (the reference: 9 + len(samples) + len(pasts) `.item()`s).
+  Args:
+    grad_sampleds, grad_honests, grad_attacks  Lists of CUDA gradients (the attack list may be empty)
+    grad_defense  The aggregated gradient
+    pasts         Iterable of (gradient, norm) of the past sampled averages, most recent first
+    momentum      args.momentum
+  Returns:
+    dict with the reference's variable names (attack.py:846-866) """
+  nan = math.nan
+  pasts = list(pasts)
+  ns, nh, na = len(grad_sampleds), len(grad_honests), len(grad_attacks)
+  s_avg, s_stats = avg_dev_max_async(grad_sampleds)
+  same = nh == ns and all(a is b for a, b in zip(grad_sampleds, grad_honests))      # attack.py:808 without momentum placement
+  h_avg, h_stats = (s_avg, s_stats) if same else avg_dev_max_async(grad_honests)
+  have_attack = na > 0
+  a_avg, a_stats = avg_dev_max_async(grad_attacks) if have_attack else (None, s_stats[:0])
+  # one vector against many, three times; every result lands in one device vector read once
+  first = [h_avg] + ([a_avg] if have_attack else []) + [grad_defense] + [g for g, _ in pasts]
+  second = ([a_avg] if have_attack else []) + [grad_defense]
+  host = torch.cat([s_stats, h_stats, a_stats, rowdots_async(s_avg, first), rowdots_async(h_avg, second),
+                    rowdots_async(grad_defense, second), grad_defense.abs().max().double().reshape(1)]).tolist()    # the only synchronisation
+  _, s_norm, s_dev, s_max = _study_tuple(None, host[:2 + ns], ns)
+  _, h_norm, h_dev, h_max = _study_tuple(None, host[2 + ns:4 + ns + nh], nh)
+  if have_attack:
+    _, a_norm, a_dev, a_max = _study_tuple(None, host[4 + ns + nh:6 + ns + nh + na], na)
+    dots = host[6 + ns + nh + na:]
+  else:
+    a_norm = a_dev = a_max = nan
+    dots = host[4 + ns + nh:]
+  k = 0
+  sh = dots[k]; k += 1
+  sa = dots[k] if have_attack else nan; k += 1 if have_attack else 0
+  sd = dots[k]; k += 1
+  past_dots = dots[k:k + len(pasts)]; k += len(pasts)
+  ha = dots[k] if have_attack else nan; k += 1 if have_attack else 0
+  hd = dots[k]; k += 1
+  ad = dots[k] if have_attack else nan; k += 1 if have_attack else 0
+  dd = dots[k]; k += 1
+  d_max = dots[k]
+  d_norm = ctypes.c_float(math.sqrt(dd)).value            # Tensor.norm() is an fp32 value (attack.py:851)
+  f32 = lambda x: ctypes.c_float(x).value                 # torch.dot(...).div_().div_().item(): fp32 arithmetic
+  def div(a, b):                                          # IEEE division (a zero norm gives inf / nan, as div_ does)
+    try:
+      return f32(a / b)
+    except ZeroDivisionError:
+      return nan if a == 0 or math.isnan(a) else math.copysign(math.inf, a) * math.copysign(1., b)
+  cos = lambda dot, na, nb: div(div(f32(dot), na), nb)
+  out = dict(sampled_grad_avg=s_avg, sampled_norm_avg=s_norm, sampled_norm_dev=s_dev, sampled_norm_max=s_max,
+             honest_grad_avg=h_avg, honest_norm_avg=h_norm, honest_norm_dev=h_dev, honest_norm_max=h_max,
+             attack_grad_avg=a_avg, attack_norm_avg=a_norm, attack_norm_dev=a_dev, attack_norm_max=a_max,
+             defense_norm_avg=d_norm, defense_norm_max=f32(d_max),
+             cosin_splhon=cos(sh, s_norm, h_norm), cosin_splatt=cos(sa, s_norm, a_norm) if have_attack else nan,
+             cosin_spldef=cos(sd, s_norm, d_norm), cosin_honatt=cos(ha, h_norm, a_norm) if have_attack else nan,
+             cosin_hondef=cos(hd, h_norm, d_norm), cosin_attdef=cos(ad, a_norm, d_norm) if have_attack else nan)
+  if pasts:
+    out["cosin_sampled"] = cos(past_dots[0], s_norm, pasts[0][1])
+    out["curv_sampled"] = momentum * sum((momentum ** i) * f32(dot) for i, dot in enumerate(past_dots))
+  else:
+    out["cosin_sampled"] = nan
+    out["curv_sampled"] = nan
+  return out
 
 # ---------------------------------------------------------------------------- #
 # Phases of the d-sharded multi-GPU path (device tensors only)

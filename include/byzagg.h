@@ -205,6 +205,13 @@ BZ_API int bz_bulyan_reduce(const float* const* rows, int n, int f, int m, const
 BZ_API int bz_avg_dev_max(const float* const* rows, int n, int64_t d, float* avg, double* stats,
                           void* ws, size_t ws_bytes, void* stream);
 
+/* ---- Dot products of the study step (attack.py:854-866: 6 cosines + up to 20 dot products with past
+ * gradients, each a `torch.dot(...).item()` with its own pass and host sync): out[i] = sum_k rows[i][k] *
+ * center[k] for all n rows in ONE pass (fp32 products accumulated in fp32 over <= 32 terms, then fp64;
+ * deterministic).  out: device double[n].  The caller reads the results with one copy. */
+BZ_API int bz_rowdots(const float* const* rows, int n, const float* center, int64_t d, double* out,
+                      void* ws, size_t ws_bytes, void* stream);
+
 /* ---- Gradient production: attack.py:776-780 / 791-795 (clip + clone per
  * worker) and :799-810 (momentum placement) for ONE worker gradient, in one pass.
  *   grad      device fp32[d], the model's flat gradient (read only)

@@ -62,6 +62,14 @@ FUSED = {
   "fuse-server": ("b200-trmean", 11, 3, "server", "0.5"),
   "fuse-noclip": ("b200-median", 11, 3, "worker", None),
 }
+# the study block (attack.py:846-866) as ONE engine.study_step call (tools/drive_attack.py --fuse-study):
+# tag -> (rule, n, f, real Byzantine workers, momentum placement)
+STUDY = {
+  "study-krum": ("b200-krum", 11, 3, 3, "update"),
+  "study-bulyan-worker": ("b200-bulyan", 11, 2, 2, "worker"),
+  "study-trmean-server": ("b200-trmean", 11, 4, 4, "server"),
+  "study-no-attack": ("b200-median", 11, 4, 0, "update"),        # no attack gradients: NaN columns (attack.py:855-859)
+}
 INFLUENCE = ("krum", "brute", "aksel", "cge", "average")
 
 @pytest.fixture(scope="module")
@@ -78,6 +86,13 @@ def runs(tmp_path_factory):
     extra = [] if clip is None else ["--gradient-clip", clip]
     jobs.append(dict(tag=tag, install_tools=True, fuse_gradients=True, args=_args(tmp / tag, gar, n, f, ["factor:1.1"], momentum_at=where)[:-2] + extra + ["--result-directory", str(tmp / tag)]))
     jobs.append(dict(tag=tag + "/stock", install_tools=True, fuse_gradients=False, args=_args(tmp / (tag + "-stock"), gar, n, f, ["factor:1.1"], momentum_at=where)[:-2] + extra + ["--result-directory", str(tmp / (tag + "-stock"))]))
+  for tag, (gar, n, f, real, where) in STUDY.items():
+    for suffix, fused in (("", True), ("/stock", False)):
+      out = tmp / (tag + ("" if fused else "-stock"))
+      argv = _args(out, gar, n, f, ["factor:1.1"], momentum_at=where)
+      argv[argv.index("--nb-real-byz") + 1] = str(real)
+      argv[argv.index("--nb-for-study") + 1] = str(n - real)
+      jobs.append(dict(tag=tag + suffix, install_tools=False, fuse_study=fused, args=argv))
   batch = tmp / "batch.json"
   batch.write_text(json.dumps(jobs))
   cmd = [sys.executable, str(ROOT / "tools" / "drive_attack.py"), "--count-calls", "--install-tools", "--batch", str(batch)]
@@ -85,7 +100,7 @@ def runs(tmp_path_factory):
   assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
   result = {}
   for job in jobs:
-    result[job["tag"]] = dict(ok=False, calls={}, rows=None, dir=pathlib.Path(job["args"][-1]), pushes=0)
+    result[job["tag"]] = dict(ok=False, calls={}, rows=None, dir=pathlib.Path(job["args"][-1]), pushes=0, studies=0)
   for line in proc.stdout.splitlines():
     if line.startswith("run-ok "):
       result[line.split()[1]]["ok"] = True
@@ -93,6 +108,8 @@ def runs(tmp_path_factory):
       result[line.split()[1]]["error"] = line
     elif line.startswith("fused-pushes "):
       result[line.split()[1]]["pushes"] = int(line.split()[2])
+    elif line.startswith("fused-studies "):
+      result[line.split()[1]]["studies"] = int(line.split()[2])
     elif line.startswith("gar-calls "):
       _, tag, name, calls, infl = line.split()
       result[tag]["calls"][name] = (int(calls), int(infl))
@@ -156,3 +173,18 @@ def test_attack_py_with_fused_gradient_production(runs, tag):
   assert theirs["ok"], theirs.get("error")
   assert mine["pushes"] == STEPS * (n - f) and theirs["pushes"] == 0        # nb_for_study = nb_honests = n - f gradients per step
   _same_study(mine["rows"], theirs["rows"], gar[5:] in INFLUENCE, rel=5e-4)
+
+@pytest.mark.parametrize("tag", sorted(STUDY))
+def test_attack_py_with_fused_study_step(runs, tag):
+  """ attack.py:846-866 (three compute_avg_dev_max, the defense norm, six cosines, the
+  past cosine, the curvature: 9 + nb_for_study_past host syncs plus those of the stock compute_avg_dev_max)
+  executed as ONE `engine.study_step` call with one host read, inside the otherwise unmodified attack.py
+  against the run with the STOCK study code: the same study file up to float rounding. """
+  gar, n, f, real, where = STUDY[tag]
+  mine, theirs = runs[tag], runs[tag + "/stock"]
+  assert mine["ok"], mine.get("error", runs["__stdout__"][-3000:])
+  assert theirs["ok"], theirs.get("error")
+  assert mine["studies"] == STEPS and theirs["studies"] == 0
+  _same_study(mine["rows"], theirs["rows"], real > 0 and gar[5:] in INFLUENCE, rel=5e-4)
+  if real == 0:        # the attack columns are NaN in both runs (checked equal above): make sure they are there
+    assert any(math.isnan(float(x)) for x in mine["rows"][0][2:-1])

@@ -110,3 +110,23 @@ def test_cuda_rule_inside_attack_py_fails_loudly_without_a_gpu(tmp_path):
   proc = _drive(tmp_path, "b200-krum")
   assert proc.returncode != 0
   assert "no CUDA device available" in proc.stdout + proc.stderr
+
+@pytest.mark.skipif(not (REF / "attack.py").exists(), reason="reference not present on this box")
+def test_in_memory_rewrites_of_attack_py_match_their_anchors_and_compile():
+  """ tools/drive_attack.py --fuse-gradients / --fuse-study: every anchor is found exactly as often as
+  expected in the reference's attack.py, the study block has the known digest, the rewritten source
+  compiles and calls the helper; a source that differs is refused. """
+  import importlib.util
+  spec = importlib.util.spec_from_file_location("drive_attack", ROOT / "tools" / "drive_attack.py")
+  drive = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(drive)
+  source = (REF / "attack.py").read_text()
+  both = drive.rewrite(source, True, True)
+  compile(both, "attack.py", "exec")
+  assert both.count("__bz_rows.push(") == 2 and both.count("__bz_rows.study(") == 1
+  assert "cosin_splhon = torch.dot" not in both and "cosin_splhon = torch.dot" in drive.rewrite(source, True, False)
+  assert "grad_pasts.appendleft(PastGrad(sampled_grad_avg, sampled_norm_avg))" in both          # the statement after the block stays
+  with pytest.raises(SystemExit):
+    drive.rewrite(source.replace("cosin_hondef = ", "cosin_hondef  = "), False, True)
+  with pytest.raises(SystemExit):
+    drive.rewrite(source.replace("grad.clone().detach_()", "grad.clone()"), True, False)

@@ -1,8 +1,6 @@
 set -x
 mkdir -p gpurun_out
-L=byzantinemomentum_b200
-( timeout 600 python tools/abbench.py --dist $L/libbyzagg.so $L/libbyzagg-notrig.so 2>&1 | tail -8 ) > gpurun_out/r2_ab_trigger.log 2>&1
-( timeout 200 python tools/k2_ab.py --cases 25:1310922,25:36489290 --no-alias --only ring 2>&1 | tail -3 ) > gpurun_out/r2_k2_now.log 2>&1
-( BYZAGG_LIBRARY=$PWD/$L/libbyzagg-notrig.so timeout 200 python tools/k2_ab.py --cases 25:1310922,25:36489290 --no-alias --only ring 2>&1 | tail -3 ) > gpurun_out/r2_k2_notrig.log 2>&1
-nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > gpurun_out/r2_clocks.txt
-cat gpurun_out/r2_ab_trigger.log gpurun_out/r2_k2_now.log gpurun_out/r2_k2_notrig.log gpurun_out/r2_clocks.txt
+( timeout 900 python -m pytest tests/test_cuda_study_step.py tests/test_attack_py_gpu.py -q -m gpu -x 2>&1 | tail -30 ) > gpurun_out/r2_t17.log 2>&1
+( timeout 300 python tools/study_time.py 2>&1 | tail -6 ) > gpurun_out/r2_study_time.txt
+( timeout 300 python tools/study_time.py 25 36489290 2 2>&1 | tail -6 ) >> gpurun_out/r2_study_time.txt
+tail -12 gpurun_out/r2_t17.log; cat gpurun_out/r2_study_time.txt

@@ -17,6 +17,7 @@ Nothing in the reference is modified; no file of it is copied.
 """
 
 import argparse
+import hashlib
 import pathlib
 import runpy
 import sys
@@ -49,12 +50,31 @@ MOMENTUM_NEW = """    if args.momentum_at == "worker":
       grad_honests = __bz_rows.honests_server(grad_momentum_server, grad_sampleds, args)
 """
 
+# The study block (attack.py:846-866) is located by the two comment lines that bracket it and checked
+# by the digest of what lies between them: nothing is rewritten unless it is exactly the known text.
+STUDY_BEGIN = "      # Compute the sampled and honest gradients norm average, norm deviation and max absolute coordinate\n"
+STUDY_END = "      # Store the new past gradient (automatic rolling)\n"
+STUDY_SHA256 = "be291ae9bc7ca4313c63ede421a64febc8c89cb15301cd16a8231a088f7d8b4f"
+STUDY_NEW = """      # (byzantinemomentum_b200) the averages, norms, cosines and the curvature of this step in a handful of
+      # device passes and one host read
+      globals().update(__bz_rows.study(grad_sampleds, grad_honests, grad_attacks, grad_defense, grad_pasts, args))
+"""
+
 class FusedRows:
   """ What the rewritten statements call.  CUDA gradients go through `GradientStack.push` (one
   kernel per worker); anything else runs the reference's own statements, unchanged. """
   def __init__(self, bz, torch):
     self.bz, self.torch, self.stack, self.fused = bz, torch, None, False
     self.pushes = 0
+    self.studies = 0
+  def study(self, sampleds, honests, attacks, defense, pasts, args):
+    """ attack.py:846-866 -> engine.study_step (CUDA gradients only: the product has no CPU path). """
+    if not defense.is_cuda:
+      raise SystemExit("drive_attack --fuse-study: the study step runs on CUDA gradients only (use --device cuda:N)")
+    self.studies += 1
+    out = self.bz.engine.study_step(sampleds, honests, attacks, defense, [(p.grad, p.norm) for p in pasts], args.momentum)
+    out["defense_grad"] = defense
+    return out
   def push(self, i, grad, args, g):
     if not grad.is_cuda:
       self.fused = False
@@ -88,16 +108,28 @@ class FusedRows:
       return self.stack.honest(args.nb_honests)
     return [grad.mul(1. - args.dampening).add_(server, alpha=args.momentum) for grad in sampleds[:args.nb_honests]]
 
-def run_attack(path, fuse, helper):
-  """ `python3 attack.py` (sys.argv already set): plain runpy, or — with `fuse` — the same source
-  with the two statement groups above swapped in memory.  Each anchor must occur exactly as often
-  as in the reference (2 and 1), else nothing runs. """
-  if not fuse:
+def rewrite(source, fuse, fuse_study):
+  """ The source of attack.py with the statement groups above swapped.  Each anchor must occur exactly
+  as often as in the reference (2 and 1; the study block once, with the known digest), else SystemExit. """
+  if fuse:
+    if source.count(CLIP_AND_CLONE) != 2 or source.count(MOMENTUM) != 1:
+      raise SystemExit("drive_attack: attack.py does not contain the expected statements; refusing to rewrite")
+    source = source.replace(CLIP_AND_CLONE, CLIP_AND_CLONE_NEW).replace(MOMENTUM, MOMENTUM_NEW)
+  if fuse_study:
+    if source.count(STUDY_BEGIN) != 1 or source.count(STUDY_END) != 1:
+      raise SystemExit("drive_attack: attack.py does not contain the expected study block; refusing to rewrite")
+    lo, hi = source.index(STUDY_BEGIN), source.index(STUDY_END)
+    if lo >= hi or hashlib.sha256(source[lo:hi].encode()).hexdigest() != STUDY_SHA256:
+      raise SystemExit("drive_attack: the study block of attack.py is not the known one; refusing to rewrite")
+    source = source[:lo] + STUDY_NEW + source[hi:]
+  return source
+
+def run_attack(path, fuse, helper, fuse_study=False):
+  """ `python3 attack.py` (sys.argv already set): plain runpy, or — with `fuse` / `fuse_study` — the
+  same source with the statement groups above swapped in memory (`rewrite`). """
+  if not fuse and not fuse_study:
     return runpy.run_path(str(path), run_name="__main__")
-  source = path.read_text()
-  if source.count(CLIP_AND_CLONE) != 2 or source.count(MOMENTUM) != 1:
-    raise SystemExit("drive_attack: attack.py does not contain the expected statements; refusing to rewrite")
-  source = source.replace(CLIP_AND_CLONE, CLIP_AND_CLONE_NEW).replace(MOMENTUM, MOMENTUM_NEW)
+  source = rewrite(path.read_text(), fuse, fuse_study)
   scope = {"__name__": "__main__", "__file__": str(path), "__builtins__": __builtins__, "__bz_rows": helper}
   exec(compile(source, str(path), "exec"), scope)
   return scope
@@ -111,6 +143,8 @@ def main():
   parser.add_argument("--install-tools", action="store_true", help="also swap tools.compute_avg_dev_max for CUDA samples")
   parser.add_argument("--fuse-gradients", action="store_true",
     help="execute attack.py with its per-worker clip/clone/momentum statements (attack.py:775-780, 790-795, 799-808) replaced IN MEMORY by GradientStack.push (the file on disk is not touched; every anchor must match exactly)")
+  parser.add_argument("--fuse-study", action="store_true",
+    help="execute attack.py with its study block (attack.py:846-866: three compute_avg_dev_max, the defense norm, six cosines, the past cosine and the curvature: 9 + nb_for_study_past host syncs) replaced IN MEMORY by engine.study_step (one host read for all dot products)")
   parser.add_argument("--batch", default=None, help="JSON file with a list of {tag, args}: run attack.py once per entry in this process")
   parser.add_argument("rest", nargs=argparse.REMAINDER, help="arguments of attack.py (after --)")
   args = parser.parse_args()
@@ -178,10 +212,12 @@ def main():
       tools.compute_avg_dev_max = cuda_study if job.get("install_tools", True) else stock_study
       try:
         helper = FusedRows(bz, torch)
-        run_attack(ref / "attack.py", bool(job.get("fuse_gradients", args.fuse_gradients)), helper)
+        run_attack(ref / "attack.py", bool(job.get("fuse_gradients", args.fuse_gradients)), helper, bool(job.get("fuse_study", args.fuse_study)))
         stream.write(f"run-ok {job['tag']}\n")
         if helper.pushes:
           stream.write(f"fused-pushes {job['tag']} {helper.pushes}\n")
+        if helper.studies:
+          stream.write(f"fused-studies {job['tag']} {helper.studies}\n")
       except BaseException as err:      # attack.py reports fatal errors through exit(1)
         stream.write(f"run-failed {job['tag']} {type(err).__name__}: {err}\n")
         traceback.print_exc(file=stream)
@@ -190,11 +226,13 @@ def main():
   sys.argv = [str(ref / "attack.py")] + rest
   helper = FusedRows(bz, torch)
   try:
-    run_attack(ref / "attack.py", args.fuse_gradients, helper)
+    run_attack(ref / "attack.py", args.fuse_gradients, helper, args.fuse_study)
   finally:
     report("run")
     if helper.pushes:
       stream.write(f"fused-pushes run {helper.pushes}\n")
+    if helper.studies:
+      stream.write(f"fused-studies run {helper.studies}\n")
 
 if __name__ == "__main__":
   main()
