@@ -164,6 +164,69 @@ int bz_average_selected(const float* const* rows, int n, const int32_t* sel, int
   return run_average_selected(rows, n, sel, count, zero_init, (float)divisor, status, d, out, (cudaStream_t)stream);
 }
 
+// Host buffers in, host buffer out, for the coordinate-wise rules: every coordinate is independent, so
+// the vector is cut into `chunks` column ranges and the three engines of the GPU work at once — while
+// chunk c+1 crosses PCIe host->device (in_stream), chunk c is reduced (stream) and the result of chunk
+// c-1 crosses device->host (out_stream; PCIe is full duplex).  The step then costs the H2D time of the
+// n rows plus the kernel and the D2H of ONE chunk, instead of H2D + kernel + D2H of the whole vector.
+int bz_coordinate_host(int rule, const float* const* host_rows, int n, int f, int64_t d, float* host_out,
+                       float* staging, int64_t pitch, float* dev_out, int chunks,
+                       void* stream, void* in_stream, void* out_stream) {
+  if (rule < BZ_RULE_AVERAGE || rule > BZ_RULE_MEAMED) return fail(BZ_EINVAL, "bz_coordinate_host: unknown rule %d", rule);
+  if (int rc = check_rows(host_rows, n, d, host_out, "bz_coordinate_host")) return rc;
+  if (rule >= BZ_RULE_TRMEAN) if (int rc = check_f_trim(n, f, "bz_coordinate_host")) return rc;
+  if (d == 0) return BZ_OK;
+  if (staging == nullptr || dev_out == nullptr) return fail(BZ_EINVAL, "bz_coordinate_host: staging / dev_out is NULL");
+  if (pitch < d || pitch % 4 != 0) return fail(BZ_EINVAL, "bz_coordinate_host: pitch = %lld must be >= d and a multiple of 4 floats", (long long)pitch);
+  if (chunks < 1 || chunks > BZ_MAX_HOST_CHUNKS) return fail(BZ_EINVAL, "bz_coordinate_host: chunks = %d outside 1..%d", chunks, BZ_MAX_HOST_CHUNKS);
+  cudaStream_t st = (cudaStream_t)stream, sin = (cudaStream_t)in_stream, sout = (cudaStream_t)out_stream;
+  // every distinct host row is staged once (the attack rows of the reference are one tensor f times)
+  int slot[kMaxN], first[kMaxN], u = 0;
+  for (int i = 0; i < n; ++i) {
+    int k = 0;
+    while (k < u && host_rows[first[k]] != host_rows[i]) ++k;
+    if (k == u) first[u++] = i;
+    slot[i] = k;
+  }
+  int64_t cs = (d + chunks - 1) / chunks;
+  cs = (cs + 63) / 64 * 64;                       // chunk starts keep the 256-byte alignment of the staged rows
+  cudaEvent_t ev[2 * BZ_MAX_HOST_CHUNKS + 2];
+  int nev = 0;
+  auto event_on = [&](cudaStream_t s) -> cudaEvent_t {
+    cudaEvent_t e = nullptr;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventRecord(e, s);
+    ev[nev++] = e;
+    return e;
+  };
+  int rc = BZ_OK;
+  // the previous user of the staging rows and of dev_out (work queued on `stream`) must be done
+  if (sin != st) cudaStreamWaitEvent(sin, event_on(st), 0);
+  const float* dev_rows[kMaxN];
+  for (int64_t c0 = 0; c0 < d && rc == BZ_OK; c0 += cs) {
+    const int64_t cnt = (d - c0 < cs) ? d - c0 : cs;
+    for (int k = 0; k < u; ++k)
+      cudaMemcpyAsync(staging + (size_t)k * pitch + c0, host_rows[first[k]] + c0, (size_t)cnt * sizeof(float), cudaMemcpyHostToDevice, sin);
+    if (sin != st) cudaStreamWaitEvent(st, event_on(sin), 0);
+    for (int i = 0; i < n; ++i) dev_rows[i] = staging + (size_t)slot[i] * pitch + c0;
+    switch (rule) {
+      case BZ_RULE_AVERAGE: rc = bz_average(dev_rows, n, cnt, dev_out + c0, stream); break;
+      case BZ_RULE_MEDIAN:  rc = bz_median(dev_rows, n, cnt, dev_out + c0, stream); break;
+      case BZ_RULE_TRMEAN:  rc = bz_trmean(dev_rows, n, f, cnt, dev_out + c0, stream); break;
+      case BZ_RULE_PHOCAS:  rc = bz_phocas(dev_rows, n, f, cnt, dev_out + c0, stream); break;
+      default:              rc = bz_meamed(dev_rows, n, f, cnt, dev_out + c0, stream); break;
+    }
+    if (rc != BZ_OK) break;
+    if (sout != st) cudaStreamWaitEvent(sout, event_on(st), 0);
+    cudaMemcpyAsync(host_out + c0, dev_out + c0, (size_t)cnt * sizeof(float), cudaMemcpyDeviceToHost, sout);
+  }
+  // whoever synchronises `stream` afterwards has the whole result
+  if (sout != st) cudaStreamWaitEvent(st, event_on(sout), 0);
+  for (int k = 0; k < nev; ++k) cudaEventDestroy(ev[k]);      // released by the runtime once they have completed
+  if (rc != BZ_OK) return rc;
+  return check_launch("bz_coordinate_host");
+}
+
 }  // extern "C"
 
 #include "api_dist.inc"

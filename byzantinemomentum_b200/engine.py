@@ -75,8 +75,10 @@ class _HostPath:
   """ How host rows reach the GPU is decided by MEASUREMENT, per device: the right answer differs between
   boxes of the same model (profiles/README.md: pinned rows on the far socket copy at 8.5 GB/s on one
   stream and at 53 GB/s on four; on other boxes four streams are the slow ones).  Candidates:
-    "lanes"  the row copies spread over 4 streams,
-    "lane"   the row copies on the current stream.
+    "lanes"     the row copies spread over 4 streams,
+    "lane"      the row copies on the current stream,
+    "pipeline"  (coordinate-wise rules only) `bz_coordinate_host`: the vector cut into column chunks, the
+                H2D copy of chunk c+1, the kernel of chunk c and the D2H copy of chunk c-1 running at once.
   (A third one — no staging, the kernel reading the pinned rows in place over PCIe — measured the same
   2.7 ms as the copies and needs `Tensor.is_pinned()`, which costs ~1 ms PER TENSOR on some boxes: dropped.)
   The first calls try each candidate twice (wall clock of the whole call: it ends with a
@@ -88,7 +90,10 @@ class _HostPath:
     key = (single_pass, pinned)
     if key in self.best:
       return self.best[key]
-    candidates = ["lanes", "lane"]
+    candidates = ["lanes", "lane"] + (["pipeline"] if single_pass else [])
+    if forced_host_path is not None and forced_host_path in candidates:
+      self.best[key] = forced_host_path
+      return forced_host_path
     seen = self.times.setdefault(key, {})
     for mode in candidates:
       if len(seen.get(mode, ())) < 2:          # two samples each: the first one pays one-time costs
@@ -101,6 +106,9 @@ class _HostPath:
       self.times.setdefault(key, {}).setdefault(mode, []).append(seconds)
 
 _host_paths = {}
+forced_host_path = None      # tests / A-B runs: pin the host path ("lanes", "lane", "pipeline") instead of measuring
+_PIPELINE_CHUNKS = 8
+_RULE_CODES = dict(average=0, median=1, trmean=2, phocas=3, meamed=4)      # BZ_RULE_*
 
 def host_path_report(device_index=None):
   """ What the measurement found (bench / tests): {(single_pass, pinned): {"best": mode, "ms": {mode: best ms}}}. """
@@ -109,7 +117,8 @@ def host_path_report(device_index=None):
   hp = _host_paths.get(device_index)
   if hp is None:
     return {}
-  return {f"single_pass={k[0]},pinned={k[1]}": dict(best=hp.best.get(k), ms={m: round(min(v) * 1e3, 3) for m, v in t.items() if v}) for k, t in hp.times.items()}
+  keys = list(dict.fromkeys(list(hp.times) + list(hp.best)))
+  return {f"single_pass={k[0]},pinned={k[1]}": dict(best=hp.best.get(k), ms={m: round(min(v) * 1e3, 3) for m, v in hp.times.get(k, {}).items() if v}) for k in keys}
 
 def _copy_streams(device):
   lanes = _copy_lanes.get(device.index)
@@ -284,7 +293,42 @@ def _raise_status(code):
 # ---------------------------------------------------------------------------- #
 # Coordinate-wise rules
 
+def _coordinate_pipeline(name, gradients, f, path, device):
+  """ Host rows in, host vector out through `bz_coordinate_host` (column chunks; copies and kernels overlap). """
+  t0 = time.perf_counter()
+  n, d = len(gradients), gradients[0].shape[0]
+  rows = [g if g.is_contiguous() else g.contiguous() for g in gradients]
+  pitch = (d + 63) // 64 * 64
+  key = (device.index, n, d)
+  buf = _staging.get(key)
+  if buf is None or buf.shape[0] < n:
+    _staging.clear()
+    buf = _staging[key] = torch.empty((n, pitch), dtype=torch.float32, device=device)
+  out = torch.empty(d, dtype=torch.float32, device=device)
+  result = torch.empty(d, dtype=torch.float32, pin_memory=True)
+  current = torch.cuda.current_stream(device)
+  lanes = _copy_streams(device)
+  ptrs = (ctypes.c_void_p * n)(*[g.data_ptr() for g in rows])
+  with _on(device):
+    code = _lib.lib().bz_coordinate_host(_RULE_CODES[name], ptrs, n, 0 if f is None else int(f), d, result.data_ptr(),
+                                         buf.data_ptr(), pitch, out.data_ptr(), _PIPELINE_CHUNKS,
+                                         current.cuda_stream, lanes[0].cuda_stream, lanes[1].cuda_stream)
+  _lib.check(code, "bz_coordinate_host")
+  current.synchronize()           # the host rows, `out` and the staging rows stay alive until here
+  path.record(True, False, "pipeline", time.perf_counter() - t0)
+  return result
+
 def _coordinate(name, gradients, f=None):
+  if type(gradients) in (list, tuple) and len(gradients) > 0 and isinstance(gradients[0], torch.Tensor) and gradients[0].device.type == "cpu" and torch.cuda.is_available():
+    _validate(gradients)
+    _lib.lib()
+    device = torch.device("cuda", torch.cuda.current_device())
+    path = _host_paths.get(device.index)
+    if path is None:
+      path = _host_paths[device.index] = _HostPath()
+    if path.choose(True, False) == "pipeline":
+      torch.cuda.current_stream(device).synchronize()        # the clock times this call only
+      return _coordinate_pipeline(name, gradients, f, path, device)
   prep = _prepare(gradients, single_pass=True)
   out = torch.empty(prep.d, dtype=torch.float32, device=prep.device)
   fn = getattr(_lib.lib(), "bz_" + name)

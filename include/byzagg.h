@@ -82,6 +82,28 @@ BZ_API int bz_phocas(const float* const* rows, int n, int f, int64_t d, float* o
 /* aggregators/trmean.py:35-50,96-109 — mean of the n-f values closest to the median. */
 BZ_API int bz_meamed(const float* const* rows, int n, int f, int64_t d, float* out, void* stream);
 
+/* ---- Host buffers in, host buffer out (the reference's `--device-gar` hop, attack.py:811-815 and
+ * :824-827: `[g.to(device_gar) for g in gradients]` ... `grad_defense.to(device)`), coordinate-wise rules.
+ * The vector is cut into `chunks` column ranges: chunk c+1 is copied host->device on `in_stream` while chunk c
+ * is reduced on `stream` and chunk c-1 returns device->host on `out_stream`, so a step costs the H2D time of the
+ * rows plus the kernel and the D2H of ONE chunk.  Same result as the whole-vector call (coordinates are
+ * independent).  Asynchronous: the result is complete once `stream` is synchronised.
+ *   rule        BZ_RULE_*; f is ignored by AVERAGE / MEDIAN
+ *   host_rows   n HOST pointers (pinned memory for full PCIe rate; equal pointers are staged once)
+ *   host_out    HOST fp32[d]
+ *   staging     DEVICE fp32[n][pitch] scratch (pitch >= d, multiple of 4; 64 keeps 256-byte row alignment)
+ *   dev_out     DEVICE fp32[d] scratch
+ *   in_stream / out_stream  copy streams (may equal `stream`: then everything is serial) */
+#define BZ_RULE_AVERAGE 0
+#define BZ_RULE_MEDIAN  1
+#define BZ_RULE_TRMEAN  2
+#define BZ_RULE_PHOCAS  3
+#define BZ_RULE_MEAMED  4
+#define BZ_MAX_HOST_CHUNKS 32
+BZ_API int bz_coordinate_host(int rule, const float* const* host_rows, int n, int f, int64_t d, float* host_out,
+                              float* staging, int64_t pitch, float* dev_out, int chunks,
+                              void* stream, void* in_stream, void* out_stream);
+
 /* ---- Distance-based rules, whole vector on this device ------------------------------ */
 
 /* aggregators/krum.py:31-80 — Multi-Krum.  order (n entries, may be NULL) receives all row

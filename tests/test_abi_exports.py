@@ -20,7 +20,7 @@ def test_header_declares_the_expected_entry_points():
   for must in ("bz_median", "bz_trmean", "bz_krum", "bz_bulyan", "bz_brute", "bz_aksel", "bz_cge", "bz_average",
                "bz_phocas", "bz_meamed", "bz_pairdist_partial", "bz_krum_select", "bz_average_selected", "bz_last_error"):
     assert must in names
-  assert len(names) == 34
+  assert len(names) == 35
 
 def test_library_loads_and_exports_every_symbol():
   from byzantinemomentum_b200 import _lib
@@ -76,3 +76,23 @@ def test_checks_and_bounds_mirror_the_reference():
   assert g["average"].influence(rows[:8], rows[8:]) == 3 / 11
   for name in g:
     assert all(hasattr(g[name], member) for member in ("check", "checked", "unchecked", "upper_bound", "influence"))
+
+def test_coordinate_host_rejects_bad_arguments_before_touching_the_gpu():
+  """ The argument checks of `bz_coordinate_host` run before any CUDA call: no GPU needed. """
+  import ctypes
+  from byzantinemomentum_b200 import _lib
+  lib = _lib.lib()
+  buf = (ctypes.c_float * 256)()
+  rows = (ctypes.c_void_p * 3)(*[ctypes.addressof(buf)] * 3)
+  where = ctypes.addressof(buf)
+  ok = dict(rule=2, n=3, f=1, d=64, pitch=64, chunks=4)
+  def call(**kw):
+    a = dict(ok, **kw)
+    return lib.bz_coordinate_host(a["rule"], rows, a["n"], a["f"], a["d"], where, a.get("staging", where), a["pitch"], a.get("dev_out", where), a["chunks"], None, None, None)
+  assert call(rule=7) == -1 and b"unknown rule" in lib.bz_last_error()
+  assert call(f=2) == -1                      # n - 2f < 1
+  assert call(pitch=32) == -1 and b"pitch" in lib.bz_last_error()
+  assert call(chunks=0) == -1 and call(chunks=33) == -1
+  assert call(staging=None) == -1
+  assert call(n=65) == -2
+  assert call(d=0) == 0                       # nothing to do

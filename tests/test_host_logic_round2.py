@@ -16,16 +16,30 @@ sharded = importlib.import_module("byzantinemomentum_b200.sharded")
 def test_host_path_tries_every_candidate_twice_then_keeps_the_fastest():
   path = engine._HostPath()
   seen = []
-  costs = {"lanes": 3.0, "lane": 2.0}
-  for _ in range(4):
+  costs = {"lanes": 3.0, "lane": 2.0, "pipeline": 2.5}
+  for _ in range(6):
     mode = path.choose(True, False)
     seen.append(mode)
     path.record(True, False, mode, costs[mode])
-  assert sorted(seen) == ["lane", "lane", "lanes", "lanes"]
+  assert sorted(seen) == ["lane", "lane", "lanes", "lanes", "pipeline", "pipeline"]      # coordinate-wise rules: three candidates
   assert all(path.choose(True, False) == "lane" for _ in range(5))
   path.record(True, False, "lane", 99.)             # later samples do not reopen the decision
   assert path.choose(True, False) == "lane"
-  assert path.choose(False, False) in ("lanes", "lane")     # another kind of call is measured on its own
+  seen = []
+  for _ in range(4):                                # another kind of call is measured on its own, without the pipeline
+    mode = path.choose(False, False)
+    seen.append(mode)
+    path.record(False, False, mode, 1.0)
+  assert sorted(seen) == ["lane", "lane", "lanes", "lanes"]
+
+def test_forced_host_path_is_used_without_sampling():
+  path = engine._HostPath()
+  engine.forced_host_path = "pipeline"
+  try:
+    assert path.choose(True, False) == "pipeline"
+    assert path.choose(False, False) == "lanes"     # not a candidate there: measured as usual
+  finally:
+    engine.forced_host_path = None
 
 def test_study_memo_matches_only_the_same_unmodified_tensor_objects():
   memo = engine._StudyMemo()
