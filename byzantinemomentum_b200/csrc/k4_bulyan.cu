@@ -12,6 +12,7 @@
 #include "dist.cuh"
 #include "launch.cuh"
 #include "networks_gen.cuh"
+#include "reduce.cuh"
 
 namespace bz {
 
@@ -98,35 +99,59 @@ k4_bulyan_static(const __grid_constant__ RowTable rows, const Geom g, const int3
     store_vec<VEC>(out, e0, g.d, full, res);
     return;
   }
-  float x[VEC][M_MAX];
-  if (full) {
+  // Stage 1 (bulyan.py:66-70, scores never updated): selected[i] = (0 + v[i] + ... + v[M_MAX-1]) / (M_MAX - i).
+  // The THETA chains start at different rows, so no partial sum can be shared without changing the
+  // rounding: sum(M_MAX - i) additions per coordinate (156 for n = 25, 625 for n = 51) and THETA
+  // divisions make this kernel instruction bound.  With two coordinates per thread both go through
+  // packed fp32 instructions (add.rn.f32x2: the same IEEE addition per lane) and the divisions by the
+  // compile-time row counts through `div_small2` (exact, reduce.cuh).
+  float sel[VEC][THETA];
+  if (VEC == 2) {
+    u64 xp[M_MAX];
+    if (full) {
 #pragma unroll
-    for (int k = 0; k < M_MAX; ++k) {
-      float t[VEC];
-      VecLoad<VEC>::load(rows.p[order[k]] + e0, t);
+      for (int k = 0; k < M_MAX; ++k) {
+        float t[VEC];
+        VecLoad<VEC>::load(rows.p[order[k]] + e0, t);
+        xp[k] = pack2(t[0], t[VEC - 1]);
+      }
+    } else {
 #pragma unroll
-      for (int c = 0; c < VEC; ++c) x[c][k] = t[c];
+      for (int k = 0; k < M_MAX; ++k) {
+        float t[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int64_t e = e0 + c;
+          t[c] = (e >= 0 && e < g.d) ? __ldcs(rows.p[order[k]] + e) : 0.f;
+        }
+        xp[k] = pack2(t[0], t[1]);
+      }
+    }
+    const u64 zero2 = pack2(0.f, 0.f);
+#pragma unroll
+    for (int it = 0; it < THETA; ++it) {
+      u64 acc = add2(zero2, xp[it]);
+#pragma unroll
+      for (int q = it + 1; q < M_MAX; ++q) acc = add2(acc, xp[q]);
+      unpack2(div_small2(acc, (float)(M_MAX - it)), sel[0][it], sel[VEC - 1][it]);
     }
   } else {
+    float x[M_MAX];
 #pragma unroll
-    for (int k = 0; k < M_MAX; ++k)
+    for (int k = 0; k < M_MAX; ++k) x[k] = (e0 >= 0 && e0 < g.d) ? __ldcs(rows.p[order[k]] + e0) : 0.f;
 #pragma unroll
-      for (int c = 0; c < VEC; ++c) {
-        const int64_t e = e0 + c;
-        x[c][k] = (e >= 0 && e < g.d) ? __ldcs(rows.p[order[k]] + e) : 0.f;
-      }
+    for (int it = 0; it < THETA; ++it) {
+      float acc = __fadd_rn(0.f, x[it]);
+#pragma unroll
+      for (int q = it + 1; q < M_MAX; ++q) acc = __fadd_rn(acc, x[q]);
+      sel[0][it] = div_small(acc, (float)(M_MAX - it));
+    }
   }
 #pragma unroll
   for (int c = 0; c < VEC; ++c) {
-    // Stage 1 (bulyan.py:66-70, scores never updated): selected[i] = (0 + v[i] + ... + v[M_MAX-1]) / (M_MAX - i)
     int key[THETA];
 #pragma unroll
-    for (int it = 0; it < THETA; ++it) {
-      float acc = __fadd_rn(0.f, x[c][it]);
-#pragma unroll
-      for (int q = it + 1; q < M_MAX; ++q) acc = __fadd_rn(acc, x[c][q]);
-      key[it] = float_to_key(__fdiv_rn(acc, (float)(M_MAX - it)));
-    }
+    for (int it = 0; it < THETA; ++it) key[it] = float_to_key(sel[c][it]);
     // Stage 2 (bulyan.py:78-84)
     SortNet<THETA>::run(OpsKeyMix<MixFull<THETA>>{g.one, g.mone}, key);
     float s[THETA];
@@ -145,7 +170,7 @@ k4_bulyan_static(const __grid_constant__ RowTable rows, const Geom g, const int3
       const bool in = (unsigned)(k - lstar) < (unsigned)BETA;
       acc = in ? __fadd_rn(acc, s[k]) : acc;
     }
-    const float r = __fdiv_rn(acc, (float)BETA);
+    const float r = div_small(acc, (float)BETA);
     res[c] = (med != med) ? quiet_nan() : r;
   }
   store_vec<VEC>(out, e0, g.d, full, res);

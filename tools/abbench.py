@@ -39,6 +39,8 @@ def main():
   libs = [a for a in sys.argv[1:] if not a.startswith("--")]
   if "--dist" in sys.argv:      # the distance-based rules (K2 experiments)
     cases = [("krum", 25, 5, 1310922), ("bulyan", 25, 5, 1310922), ("krum", 25, 5, 36489290), ("cge", 25, 5, 1310922), ("krum", 51, 12, 1310922)]
+  elif "--bulyan" in sys.argv:  # K4 experiments
+    cases = [("bulyan", 25, 5, 1310922), ("bulyan", 11, 2, 1310922), ("bulyan", 51, 12, 4568373), ("bulyan", 25, 5, 36489290), ("bulyan", 15, 3, 1310922), ("krum", 25, 5, 1310922)]
   else:
    cases = [("average", 25, 10, 1310922), ("median", 25, 10, 1310922), ("trmean", 25, 10, 1310922), ("trmean", 25, 7, 1310922),
            ("median", 25, 10, 36489290), ("trmean", 25, 10, 36489290), ("trmean", 25, 7, 36489290),
