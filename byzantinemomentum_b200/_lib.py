@@ -70,6 +70,7 @@ SIGNATURES = {
   "bz_rowdist_select_peers": (_i, [_c_rows, _i, _i, _i, _vp, _vp]),
   "bz_avg_dev_max": (_i, [_c_rows, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
   "bz_rowdots": (_i, [_c_rows, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
+  "bz_stage_rows": (_i, [_c_rows, _i, _i64, _vp, _i64, _vp]),
   "bz_coordinate_host": (_i, [_i, _c_rows, _i, _i, _i64, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp]),
   "bz_gradient_row": (_i, [_vp, _i64, _dbl, _vp, _i, _vp, _dbl, _dbl, _vp, _vp, _sz, _vp]),
   "bz_average_selected": (_i, [_c_rows, _i, _vp, _i, _i, _dbl, _vp, _i64, _vp, _vp]),

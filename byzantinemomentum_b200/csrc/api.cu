@@ -165,6 +165,40 @@ int bz_average_selected(const float* const* rows, int n, const int32_t* sel, int
   return run_average_selected(rows, n, sel, count, zero_init, (float)divisor, status, d, out, (cudaStream_t)stream);
 }
 
+// n host->device copies of `bytes` each as ONE batch (cudaMemcpyBatchAsync, CUDA >= 12.8; not on the
+// legacy default stream): separate cudaMemcpyAsync calls cost ~5.7 us each on the copy engine (measured:
+// n pinned rows vs one contiguous copy of the same bytes, bench.py h2d_probe).  Falls back to the loop.
+static void h2d_rows(void** dsts, void** srcs, int count, size_t bytes, cudaStream_t s) {
+  static const bool batch_allowed = [] { const char* e = getenv("BYZAGG_H2D_BATCH"); return e == nullptr || e[0] != '0'; }();
+  static bool batch_works = true;
+  if (batch_allowed && batch_works && s != nullptr && count > 1) {
+    size_t sizes[kMaxN];
+    for (int k = 0; k < count; ++k) sizes[k] = bytes;
+    cudaMemcpyAttributes attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+    size_t attr_index = 0, fail_index = 0;
+    if (cudaMemcpyBatchAsync(dsts, srcs, sizes, (size_t)count, &attr, &attr_index, 1, &fail_index, s) == cudaSuccess) return;
+    cudaGetLastError();
+    batch_works = false;          // older driver: the plain loop from now on
+  }
+  for (int k = 0; k < count; ++k) cudaMemcpyAsync(dsts[k], srcs[k], bytes, cudaMemcpyHostToDevice, s);
+}
+
+int bz_stage_rows(const float* const* host_rows, int n, int64_t d, float* staging, int64_t pitch, void* stream) {
+  if (int rc = check_rows(host_rows, n, d, staging, "bz_stage_rows")) return rc;
+  if (d == 0) return BZ_OK;
+  if (pitch < d) return fail(BZ_EINVAL, "bz_stage_rows: pitch = %lld < d = %lld", (long long)pitch, (long long)d);
+  void* dsts[kMaxN];
+  void* srcs[kMaxN];
+  for (int k = 0; k < n; ++k) {
+    dsts[k] = staging + (size_t)k * pitch;
+    srcs[k] = const_cast<float*>(host_rows[k]);
+  }
+  h2d_rows(dsts, srcs, n, (size_t)d * sizeof(float), (cudaStream_t)stream);
+  return check_launch("bz_stage_rows");
+}
+
 // Host buffers in, host buffer out, for the coordinate-wise rules: every coordinate is independent, so
 // the vector is cut into `chunks` column ranges and the three engines of the GPU work at once — while
 // chunk c+1 crosses PCIe host->device (in_stream), chunk c is reduced (stream) and the result of chunk
@@ -201,36 +235,18 @@ int bz_coordinate_host(int rule, const float* const* host_rows, int n, int f, in
     return e;
   };
   int rc = BZ_OK;
-  static const bool batch_allowed = [] { const char* e = getenv("BYZAGG_H2D_BATCH"); return e == nullptr || e[0] != '0'; }();
-  bool use_batch = batch_allowed;
   // the previous user of the staging rows and of dev_out (work queued on `stream`) must be done
   if (sin != st) cudaStreamWaitEvent(sin, event_on(st), 0);
   const float* dev_rows[kMaxN];
   for (int64_t c0 = 0; c0 < d && rc == BZ_OK; c0 += cs) {
     const int64_t cnt = (d - c0 < cs) ? d - c0 : cs;
-    // The u row copies of a chunk as ONE batch (cudaMemcpyBatchAsync, CUDA >= 12.8; not on the legacy
-    // default stream): separate cudaMemcpyAsync calls cost ~5.7 us each on the copy engine (measured:
-    // n pinned rows vs one contiguous copy of the same bytes, bench.py h2d_probe).
-    bool batched = false;
-    if (use_batch && sin != nullptr && u > 1) {
-      void* dsts[kMaxN];
-      void* srcs[kMaxN];
-      size_t sizes[kMaxN];
-      for (int k = 0; k < u; ++k) {
-        dsts[k] = staging + (size_t)k * pitch + c0;
-        srcs[k] = const_cast<float*>(host_rows[first[k]] + c0);
-        sizes[k] = (size_t)cnt * sizeof(float);
-      }
-      cudaMemcpyAttributes attr;
-      memset(&attr, 0, sizeof(attr));
-      attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
-      size_t attr_index = 0, fail_index = 0;
-      if (cudaMemcpyBatchAsync(dsts, srcs, sizes, (size_t)u, &attr, &attr_index, 1, &fail_index, sin) == cudaSuccess) batched = true;
-      else { cudaGetLastError(); use_batch = false; }       // older driver: the plain loop below
+    void* dsts[kMaxN];
+    void* srcs[kMaxN];
+    for (int k = 0; k < u; ++k) {
+      dsts[k] = staging + (size_t)k * pitch + c0;
+      srcs[k] = const_cast<float*>(host_rows[first[k]] + c0);
     }
-    if (!batched)
-      for (int k = 0; k < u; ++k)
-        cudaMemcpyAsync(staging + (size_t)k * pitch + c0, host_rows[first[k]] + c0, (size_t)cnt * sizeof(float), cudaMemcpyHostToDevice, sin);
+    h2d_rows(dsts, srcs, u, (size_t)cnt * sizeof(float), sin);
     if (sin != st) cudaStreamWaitEvent(st, event_on(sin), 0);
     for (int i = 0; i < n; ++i) dev_rows[i] = staging + (size_t)slot[i] * pitch + c0;
     switch (rule) {

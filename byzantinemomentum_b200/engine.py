@@ -77,6 +77,8 @@ class _HostPath:
   stream and at 53 GB/s on four; on other boxes four streams are the slow ones).  Candidates:
     "lanes"     the row copies spread over 4 streams,
     "lane"      the row copies on the current stream,
+    "batch"     `bz_stage_rows`: the row copies as ONE cudaMemcpyBatchAsync on a copy stream (a separate
+                cudaMemcpyAsync per row costs ~5.7 us of copy-engine time each),
     "pipeline"  (coordinate-wise rules only) `bz_coordinate_host`: the vector cut into column chunks, the
                 H2D copy of chunk c+1, the kernel of chunk c and the D2H copy of chunk c-1 running at once.
   (A third one — no staging, the kernel reading the pinned rows in place over PCIe — measured the same
@@ -90,7 +92,7 @@ class _HostPath:
     key = (single_pass, pinned)
     if key in self.best:
       return self.best[key]
-    candidates = ["lanes", "lane"] + (["pipeline"] if single_pass else [])
+    candidates = ["lanes", "lane"] + (["pipeline"] if single_pass else ["batch"])
     if forced_host_path is not None and forced_host_path in candidates:
       self.best[key] = forced_host_path
       return forced_host_path
@@ -107,7 +109,7 @@ class _HostPath:
 
 _host_paths = {}
 forced_host_path = None      # tests / A-B runs: pin the host path ("lanes", "lane", "pipeline") instead of measuring
-_PIPELINE_CHUNKS = 8
+_PIPELINE_CHUNKS = 4       # measured (profiles/r02_e2e_pipeline_ab.txt): 2 .. 8 within 1 %, 1 and 16+ slower
 _RULE_CODES = dict(average=0, median=1, trmean=2, phocas=3, meamed=4)      # BZ_RULE_*
 
 def host_path_report(device_index=None):
@@ -224,17 +226,27 @@ def _prepare(gradients, single_pass=False):
     # 53 GB/s on two or more — with one stream the e2e step took 12.5 ms, 2.5x the box's own PCIe
     # floor, and varied 4x between boxes depending on where the caller's pages happened to be.
     current = torch.cuda.current_stream(device)
-    lanes = _copy_streams(device) if mode == "lanes" else [current]
-    if mode == "lanes":
+    if mode == "batch" and not all(g.is_contiguous() for g in uniq.values()):
+      mode = "lane"
+    lanes = _copy_streams(device) if mode == "lanes" else ([_copy_streams(device)[0]] if mode == "batch" else [current])
+    if mode in ("lanes", "batch"):
       for lane in lanes:
         lane.wait_stream(current)        # the previous call's kernels have finished with the staging buffer
     slot = {}
-    for k, (ident, g) in enumerate(uniq.items()):
-      row = buf[k, :d]
-      with torch.cuda.stream(lanes[k % len(lanes)]):
-        row.copy_(g, non_blocking=True)
-      slot[ident] = row
-    if mode == "lanes":
+    if mode == "batch":
+      hosts = (ctypes.c_void_p * len(uniq))(*[g.data_ptr() for g in uniq.values()])
+      with _on(device):
+        code = _lib.lib().bz_stage_rows(hosts, len(uniq), d, buf.data_ptr(), buf.stride(0), lanes[0].cuda_stream)
+      _lib.check(code, "bz_stage_rows")
+      for k, ident in enumerate(uniq):
+        slot[ident] = buf[k, :d]
+    else:
+      for k, (ident, g) in enumerate(uniq.items()):
+        row = buf[k, :d]
+        with torch.cuda.stream(lanes[k % len(lanes)]):
+          row.copy_(g, non_blocking=True)
+        slot[ident] = row
+    if mode in ("lanes", "batch"):
       for lane in lanes:
         current.wait_stream(lane)
     rows = [slot[id(g)] for g in gradients]

@@ -71,3 +71,17 @@ def test_c_entry_serial_streams_and_one_chunk():
     _lib.check(code, "bz_coordinate_host")
     torch.cuda.synchronize()
     assert torch.equal(result, want)
+
+@pytest.mark.parametrize("name,f", [("krum", 3), ("bulyan", 2), ("cge", 3), ("aksel", 3)])
+def test_batched_staging_equals_the_device_call(name, f):
+  """ Distance-based rules on host rows: `bz_stage_rows` (one batched copy) instead of n copies. """
+  engine.forced_host_path = "batch"
+  engine._host_paths.clear()
+  n, d = 11, 79510
+  host = [torch.randn(d).pin_memory() for _ in range(n - 1)]
+  host.append(host[2])
+  want = bz.gars[name].unchecked(gradients=[h.cuda() for h in host], f=f).cpu()
+  for _ in range(2):
+    got = bz.gars[name].unchecked(gradients=host, f=f)
+    assert got.device.type == "cpu" and torch.equal(got.view(torch.int32), want.view(torch.int32))
+  assert engine.host_path_report()["single_pass=False,pinned=False"]["best"] == "batch"

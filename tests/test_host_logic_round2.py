@@ -26,11 +26,11 @@ def test_host_path_tries_every_candidate_twice_then_keeps_the_fastest():
   path.record(True, False, "lane", 99.)             # later samples do not reopen the decision
   assert path.choose(True, False) == "lane"
   seen = []
-  for _ in range(4):                                # another kind of call is measured on its own, without the pipeline
+  for _ in range(6):                                # another kind of call is measured on its own, without the pipeline
     mode = path.choose(False, False)
     seen.append(mode)
     path.record(False, False, mode, 1.0)
-  assert sorted(seen) == ["lane", "lane", "lanes", "lanes"]
+  assert sorted(seen) == ["batch", "batch", "lane", "lane", "lanes", "lanes"]
 
 def test_forced_host_path_is_used_without_sampling():
   path = engine._HostPath()
