@@ -42,6 +42,8 @@ constexpr int kRWarps = 12;             // warps (= tasks) per CTA ...
 constexpr int kRWarpsSmall = 6;         // ... or 6, two CTAs per SM, when all tasks fit 6 warps (n <= 15): a warp's 25-slot
                                         // task takes the same time per tile whatever n, so small n is bound by tiles per
                                         // SM per unit time, and two resident CTAs walk two tile streams at once
+constexpr int kRWarpsWide = 16;         // ... or 16 (four per scheduler, 128 registers) in the clusters of n > 35: the same 60 tasks of
+                                        // n = 51 then need 4 CTAs instead of 5, and 4-CTA clusters fill 144 of the 148 SMs (5-CTA: 130)
 constexpr int kRThreads = kRWarps * 32;
 constexpr int kRSlots = kG * kG;
 constexpr size_t kRSmemBudget = 226 * 1024;
@@ -58,7 +60,7 @@ constexpr int kTailTickets = 32;         // words of ticket scratch (1 + number 
 
 // Unique rows whose distance to themselves is needed (multiplicity > 1), spread over the warps.
 struct SelfList {
-  unsigned char row[kRWarps * kRMaxCluster * kSelfPerWarp];
+  unsigned char row[kRWarpsWide * kRMaxCluster * kSelfPerWarp];
   int count;
 };
 
@@ -322,7 +324,7 @@ __device__ __forceinline__ void ring_stage_tail(float* buf, const RowTable& rows
 // One CTA = 12 warps = 12 tasks; a cluster of C CTAs covers tasks [0, 12 C) of the same tiles.
 // parts[cluster * n * n + i * n + j] (i < j; i == j for the rows of `self`).
 template <int T, int STAGES, bool SELF, bool CLUSTER, int W>
-__global__ void __launch_bounds__(W * 32, W == kRWarps ? 1 : 2)
+__global__ void __launch_bounds__(W * 32, W == kRWarpsSmall ? 2 : 1)
 k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList self, const __grid_constant__ RingTail tail,
         const __grid_constant__ StarList star, const int n, const int csize, const int64_t d, const int64_t nfull,
         double* __restrict__ parts) {
@@ -662,7 +664,7 @@ static int launch_ring_cfg(const RowTable& rows, const SelfList& self, RingTail&
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
-  int nclusters = sm_count() * (W == kRWarps ? 1 : 2) / C;
+  int nclusters = sm_count() * (W == kRWarpsSmall ? 2 : 1) / C;
   if (CLUSTER) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)C;
@@ -698,11 +700,25 @@ static int launch_ring_cfg(const RowTable& rows, const SelfList& self, RingTail&
   return nclusters;
 }
 
-// Cluster size for n rows (1 when all tasks fit one CTA); 0 = not supported by this kernel.
+// Launch shape for n rows: warps per CTA and CTAs per cluster (1 when all tasks fit one CTA).
+//   n <= 15 (all tasks fit 6 warps): 6 warps, two CTAs per SM       (BYZAGG_K2_W12=1: 12, for A/B runs)
+//   n <= 25: 12 warps;   n <= 35: clusters of 12-warp CTAs
+//   n >  35: clusters of 16-warp CTAs                                (BYZAGG_K2_W16=0: 12, for A/B runs)
+// Returns false when the kernel does not support n.
+static bool ring_shape(int n, int& W, int& C) {
+  static const bool w12 = [] { const char* e = getenv("BYZAGG_K2_W12"); return e && e[0] == '1'; }();
+  static const bool w16 = [] { const char* e = getenv("BYZAGG_K2_W16"); return !(e && e[0] == '0'); }();
+  const int ng = (n + kG - 1) / kG, tasks = ring_ntasks(ng);
+  W = kRWarps;
+  if (tasks <= kRWarpsSmall && n <= 3 * kRWarpsSmall && !w12) W = kRWarpsSmall;
+  else if (ng * kG > 35 && w16) W = kRWarpsWide;
+  C = (tasks + W - 1) / W;
+  if (C < 1) C = 1;
+  return C <= kRMaxCluster;
+}
 int ring_cluster_size(int n) {
-  const int ng = (n + kG - 1) / kG;
-  const int C = (ring_ntasks(ng) + kRWarps - 1) / kRWarps;
-  return C <= kRMaxCluster ? (C < 1 ? 1 : C) : 0;
+  int W, C;
+  return ring_shape(n, W, C) ? C : 0;
 }
 
 // Returns the number of partial blocks written, or -1 when the configuration cannot run here
@@ -711,16 +727,9 @@ int launch_pairdist_ring(const RowTable& rows, int n, int64_t d, double* parts, 
                          const unsigned char* self_rows, int nself, SelectTail* select) {
   const char* env = getenv("BYZAGG_K2_CLUSTER");
   const int force_cluster = env ? atoi(env) : 0;
-  int C = ring_cluster_size(n);
-  if (C == 0) return -1;
+  int W, C;
+  if (!ring_shape(n, W, C)) return -1;
   if (force_cluster > C && force_cluster <= kRMaxCluster) C = force_cluster;   // experiments: more CTAs per tile than needed
-  // warps per CTA: 6 (two CTAs per SM) when every task fits them (n <= 15), else 12 (BYZAGG_K2_W12=1: always 12, for A/B runs)
-  const auto warps_for = [](int rows_n, int c) {
-    const char* w12 = getenv("BYZAGG_K2_W12");
-    const int g = (rows_n + kG - 1) / kG;
-    return (c == 1 && ring_ntasks(g) <= kRWarpsSmall && rows_n <= 3 * kRWarpsSmall && !(w12 && w12[0] == '1')) ? kRWarpsSmall : kRWarps;
-  };
-  const int W = warps_for(n, C);
   if (nself > W * C * kSelfPerWarp) return -1;
   for (int r = 0; r < n; ++r)
     if ((((uintptr_t)rows.p[r]) & 15) != 0) return -1;
@@ -769,9 +778,10 @@ int launch_pairdist_ring(const RowTable& rows, int n, int64_t d, double* parts, 
       int slots = 3;
       if (nfresh * ((n + slots - 1) / slots) > W * C) slots = kRSlots;
       const int chunks = (n + slots - 1) / slots;
+      int old_W = 0, old_C = 0;
       ok = ok && nfresh >= 1 && nfresh <= kStarMax && nfresh * chunks <= W * C && nfresh < n
-              && ring_cluster_size(select->u_old) == C && geometry(old_alloc, C) == geometry(rows_alloc, C)
-              && warps_for(select->u_old, C) == W;
+              && ring_shape(select->u_old, old_W, old_C) && old_C == C && old_W == W
+              && geometry(old_alloc, C) == geometry(rows_alloc, C);
       if (ok) {
         star.count = nfresh;
         star.slots = slots;
@@ -791,6 +801,8 @@ int launch_pairdist_ring(const RowTable& rows, int n, int64_t d, double* parts, 
                                           : launch_ring_cfg<512, 3, false, false, kRWarpsSmall>(rows, self, tail, star, n, C, d, parts, st);
     else                   nparts = BZ_RING(512, 4, false);
   } else if (rows_alloc <= 35) nparts = BZ_RING(512, 3, true);
+  else if (W == kRWarpsWide)   nparts = selfk ? launch_ring_cfg<256, 3, true, true, kRWarpsWide>(rows, self, tail, star, n, C, d, parts, st)
+                                              : launch_ring_cfg<256, 3, false, true, kRWarpsWide>(rows, self, tail, star, n, C, d, parts, st);
   else                         nparts = BZ_RING(256, 3, true);   // (512-column tiles with 2 stages measured 20 % slower at n = 40...51)
 #undef BZ_RING
   if (select != nullptr) {

@@ -39,6 +39,9 @@ def main():
   libs = [a for a in sys.argv[1:] if not a.startswith("--")]
   if "--dist" in sys.argv:      # the distance-based rules (K2 experiments)
     cases = [("krum", 25, 5, 1310922), ("bulyan", 25, 5, 1310922), ("krum", 25, 5, 36489290), ("cge", 25, 5, 1310922), ("krum", 51, 12, 1310922)]
+  elif "--wide" in sys.argv:    # clusters of 16-warp CTAs (n > 35)
+    cases = [("krum", 51, 12, 4568373), ("bulyan", 51, 12, 4568373), ("krum", 51, 12, 1310922), ("krum", 40, 9, 1310922), ("krum", 45, 10, 1310922),
+             ("krum", 64, 15, 1310922), ("krum", 51, 12, 36546980), ("krum", 35, 8, 1310922)]
   elif "--bulyan" in sys.argv:  # K4 experiments
     cases = [("bulyan", 25, 5, 1310922), ("bulyan", 11, 2, 1310922), ("bulyan", 51, 12, 4568373), ("bulyan", 25, 5, 36489290), ("bulyan", 15, 3, 1310922), ("krum", 25, 5, 1310922)]
   else:
@@ -48,7 +51,11 @@ def main():
   results = {}
   for rep in range(2):
     for lib in libs:
-      env = dict(os.environ, BYZAGG_LIBRARY=str(pathlib.Path(lib).resolve()))
+      # a variant is `library.so` or `library.so@NAME=VALUE` (an environment switch of the same library)
+      path, _, setting = lib.partition("@")
+      env = dict(os.environ, BYZAGG_LIBRARY=str(pathlib.Path(path).resolve()))
+      if setting:
+        env[setting.split("=", 1)[0]] = setting.split("=", 1)[1]
       proc = subprocess.run([sys.executable, "-c", CHILD, json.dumps(cases)], env=env, capture_output=True, text=True)
       line = [l for l in proc.stdout.splitlines() if l.startswith("RESULT ")]
       if not line:
@@ -56,10 +63,10 @@ def main():
         continue
       for k, v in json.loads(line[0][7:]).items():
         results.setdefault(k, {}).setdefault(lib, []).append(v)
-  names = [pathlib.Path(l).name for l in libs]
-  print("%-36s" % "case (us per call, best of 3; two runs)" + "".join("%24s" % n for n in names))
+  names = [pathlib.Path(l.partition("@")[0]).name[:12] + ("@" + l.partition("@")[2] if "@" in l else "") for l in libs]
+  print("%-36s" % "case (us per call, best of 3; two runs)" + "".join("%30s" % n for n in names))
   for k, per in results.items():
-    print("%-36s" % k + "".join("%24s" % " / ".join("%.1f" % x for x in per.get(l, [])) for l in libs))
+    print("%-36s" % k + "".join("%30s" % " / ".join("%.1f" % x for x in per.get(l, [])) for l in libs))
 
 if __name__ == "__main__":
   main()
