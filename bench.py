@@ -468,10 +468,10 @@ def run_b200(args):
     out = bz.gars[gar].unchecked(gradients=host[k % host_sets], f=f)
     assert out.device.type == "cpu"
     return out
-  for k in range(10):             # the engine measures its host->device candidates during the first calls (engine._HostPath)
+  for k in range(12):             # the engine measures its host->device candidates during the first calls (engine._HostPath)
     e2e_step(k)
   barrier()
-  e2e_total, _ = time_steps(torch, e2e_step, e2e_steps)
+  e2e_total, e2e_each = time_steps(torch, e2e_step, e2e_steps)
   if dist is not None:
     t = torch.tensor([e2e_total], device=device, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -481,7 +481,7 @@ def run_b200(args):
   e2e = dict(value=world * d / (e2e_ms * 1e-3), unit="params/s", h2d_bytes_per_step=n * d * 4, d2h_bytes_per_step=d * 4,
              h2d_probe=probe, pcie_floor_ms=probe.get("ms"), host_path=bz.engine.host_path_report(device.index), h2d_rate_achieved_gbs=n * d * 4 / (e2e_ms * 1e-3) / 1e9,
              note="pcie_floor_ms = the faster of one contiguous pinned copy and n pinned row copies of the step's bytes on THIS box, outside the library (PCIe Gen5 x16 nominal: 2.1-2.4 ms); the step adds the kernel (~23 us), the 5 MB result copy and its synchronisation; host_path 'pipeline' = bz_coordinate_host (column chunks: batched H2D of chunk c+1, kernel of chunk c and D2H of chunk c-1 overlap)",
-             ms_per_step=e2e_ms, steps=e2e_steps, host_buffers="pinned" + (", allocated under the NVML ideal-affinity binding" if numa_local else "") + "; host->device path chosen by measurement (see host_path)", call=f"byzantinemomentum_b200.gars[{gar!r}].unchecked(gradients=<{n} pinned host tensors>, f={f})")
+             ms_per_step=e2e_ms, ms_per_step_min=min(e2e_each), ms_per_step_median=sorted(e2e_each)[len(e2e_each) // 2], ms_per_step_max=max(e2e_each), steps=e2e_steps, host_buffers="pinned" + (", allocated under the NVML ideal-affinity binding" if numa_local else "") + "; host->device path chosen by measurement (see host_path)", call=f"byzantinemomentum_b200.gars[{gar!r}].unchecked(gradients=<{n} pinned host tensors>, f={f})")
   del host
 
   line = dict(metric="aggregated-params/sec", value=value, unit="params/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),

@@ -83,8 +83,8 @@ class _HostPath:
                 H2D copy of chunk c+1, the kernel of chunk c and the D2H copy of chunk c-1 running at once.
   (A third one — no staging, the kernel reading the pinned rows in place over PCIe — measured the same
   2.7 ms as the copies and needs `Tensor.is_pinned()`, which costs ~1 ms PER TENSOR on some boxes: dropped.)
-  The first calls try each candidate twice (wall clock of the whole call: it ends with a
-  synchronisation), then the fastest is kept. """
+  The first calls try each candidate three times (wall clock of the whole call: it ends with a
+  synchronisation); the first sample pays one-time costs, the slower of the other two ranks the candidate. """
   def __init__(self):
     self.times = {}
     self.best = {}
@@ -98,9 +98,10 @@ class _HostPath:
       return forced_host_path
     seen = self.times.setdefault(key, {})
     for mode in candidates:
-      if len(seen.get(mode, ())) < 2:          # two samples each: the first one pays one-time costs
+      if len(seen.get(mode, ())) < 3:          # three samples each: the first one pays one-time costs
         return mode
-    self.best[key] = min(candidates, key=lambda mode: min(seen[mode]))
+    # the median of the last two samples: a path that is fast once and slow the next time is not "the fastest"
+    self.best[key] = min(candidates, key=lambda mode: max(seen[mode][1:]))
     return self.best[key]
   def record(self, single_pass, pinned, mode, seconds):
     key = (single_pass, pinned)
@@ -120,7 +121,8 @@ def host_path_report(device_index=None):
   if hp is None:
     return {}
   keys = list(dict.fromkeys(list(hp.times) + list(hp.best)))
-  return {f"single_pass={k[0]},pinned={k[1]}": dict(best=hp.best.get(k), ms={m: round(min(v) * 1e3, 3) for m, v in hp.times.get(k, {}).items() if v}) for k in keys}
+  return {f"single_pass={k[0]},pinned={k[1]}": dict(best=hp.best.get(k), ms={m: round(min(v) * 1e3, 3) for m, v in hp.times.get(k, {}).items() if v},
+                                                           samples_ms={m: [round(x * 1e3, 3) for x in v] for m, v in hp.times.get(k, {}).items() if v}) for k in keys}
 
 def _copy_streams(device):
   lanes = _copy_lanes.get(device.index)

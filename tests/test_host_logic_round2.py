@@ -13,24 +13,32 @@ engine = importlib.import_module("byzantinemomentum_b200.engine")
 gars = importlib.import_module("byzantinemomentum_b200.gars")
 sharded = importlib.import_module("byzantinemomentum_b200.sharded")
 
-def test_host_path_tries_every_candidate_twice_then_keeps_the_fastest():
+def test_host_path_tries_every_candidate_three_times_then_keeps_the_fastest():
   path = engine._HostPath()
   seen = []
   costs = {"lanes": 3.0, "lane": 2.0, "pipeline": 2.5}
-  for _ in range(6):
+  for _ in range(9):
     mode = path.choose(True, False)
     seen.append(mode)
     path.record(True, False, mode, costs[mode])
-  assert sorted(seen) == ["lane", "lane", "lanes", "lanes", "pipeline", "pipeline"]      # coordinate-wise rules: three candidates
+  assert sorted(seen) == ["lane"] * 3 + ["lanes"] * 3 + ["pipeline"] * 3      # coordinate-wise rules: three candidates
   assert all(path.choose(True, False) == "lane" for _ in range(5))
   path.record(True, False, "lane", 99.)             # later samples do not reopen the decision
   assert path.choose(True, False) == "lane"
   seen = []
-  for _ in range(6):                                # another kind of call is measured on its own, without the pipeline
+  for _ in range(9):                                # another kind of call is measured on its own, without the pipeline
     mode = path.choose(False, False)
     seen.append(mode)
     path.record(False, False, mode, 1.0)
-  assert sorted(seen) == ["batch", "batch", "lane", "lane", "lanes", "lanes"]
+  assert sorted(seen) == ["batch"] * 3 + ["lane"] * 3 + ["lanes"] * 3
+
+def test_host_path_ranks_by_the_slower_of_the_late_samples():
+  path = engine._HostPath()
+  samples = {"lanes": [9., 3., 3.], "lane": [9., 2.6, 2.7], "pipeline": [9., 2.4, 3.5]}      # fast once, slow the next time
+  for _ in range(9):
+    mode = path.choose(True, False)
+    path.record(True, False, mode, samples[mode].pop(0))
+  assert path.choose(True, False) == "lane"
 
 def test_forced_host_path_is_used_without_sampling():
   path = engine._HostPath()
