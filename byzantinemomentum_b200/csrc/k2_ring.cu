@@ -42,8 +42,8 @@ constexpr int kRWarps = 12;             // warps (= tasks) per CTA ...
 constexpr int kRWarpsSmall = 6;         // ... or 6, two CTAs per SM, when all tasks fit 6 warps (n <= 15): a warp's 25-slot
                                         // task takes the same time per tile whatever n, so small n is bound by tiles per
                                         // SM per unit time, and two resident CTAs walk two tile streams at once
-constexpr int kRWarpsWide = 16;         // ... or 16 (four per scheduler, 128 registers) in the clusters of n > 35: the 60 tasks of n = 51
-                                        // then need 4 CTAs instead of 5; the fourth warp per scheduler raises the FMA-pipe utilisation
+constexpr int kRWarpsWide = 16;         // ... or 16 (four per scheduler, 128 registers) in the clusters of n > 35: the same 60 tasks of
+                                        // n = 51 then need 4 CTAs instead of 5, and 4-CTA clusters fill 144 of the 148 SMs (5-CTA: 130)
 constexpr int kRThreads = kRWarps * 32;
 constexpr int kRSlots = kG * kG;
 constexpr size_t kRSmemBudget = 226 * 1024;
@@ -260,105 +260,6 @@ __device__ __forceinline__ void sweep_comp(const float* x_base, const float* y_b
   }
 }
 
-// ---- split shape (16 warps, one CTA, 21 <= n <= 25): 12 main warps take 20 pairs of their task, 4 helper
-// warps take the remaining 5 pairs of three tasks each (12 x 20 + 4 x 15 = 300).  Each pair goes through
-// exactly the operations it goes through in sweep_off / sweep_comp: same lane, same steps.
-template <int T>
-__device__ __forceinline__ void sweep_off4(const float* a_base, const float* b_base, int lane, u64 (&acc)[kRSlots]) {
-#pragma unroll
-  for (int c = 0; c < T; c += 128) {
-    u64 a0[kG - 1], a1[kG - 1], b0[kG], b1[kG];
-#pragma unroll
-    for (int i = 0; i < kG - 1; ++i) {
-      const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(a_base + i * T + c + lane * 4);
-      a0[i] = t.x; a1[i] = t.y;
-    }
-#pragma unroll
-    for (int j = 0; j < kG; ++j) {
-      const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(b_base + j * T + c + lane * 4);
-      b0[j] = t.x; b1[j] = t.y;
-    }
-#pragma unroll
-    for (int i = 0; i < kG - 1; ++i)
-#pragma unroll
-      for (int j = 0; j < kG; ++j) {
-        const u64 d0 = sub2(a0[i], b0[j]), d1 = sub2(a1[i], b1[j]);
-        acc[i * kG + j] = fma2(d0, d0, acc[i * kG + j]);
-        acc[i * kG + j] = fma2(d1, d1, acc[i * kG + j]);
-      }
-  }
-}
-// the two whole diagonal blocks of a composite (slots 0..9 and 10..19 as in sweep_comp)
-template <int T>
-__device__ __forceinline__ void sweep_diag2(const float* x_base, const float* y_base, int lane, u64 (&acc)[kRSlots]) {
-#pragma unroll
-  for (int c = 0; c < T; c += 128) {
-    const int o = c + lane * 4;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const float* base = h == 0 ? x_base : y_base;
-      u64 a0[kG], a1[kG];
-#pragma unroll
-      for (int i = 0; i < kG; ++i) {
-        const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(base + i * T + o);
-        a0[i] = t.x; a1[i] = t.y;
-      }
-      int p = 10 * h;
-#pragma unroll
-      for (int i = 0; i < kG; ++i)
-#pragma unroll
-        for (int j = i + 1; j < kG; ++j) {
-          const u64 d0 = sub2(a0[i], a0[j]), d1 = sub2(a1[i], a1[j]);
-          acc[p] = fma2(d0, d0, acc[p]);
-          acc[p] = fma2(d1, d1, acc[p]);
-          ++p;
-        }
-    }
-  }
-}
-// A helper's three 5-pair units.  Unit q writes slots 5q .. 5q+4.  kind 1: row `a` (the fifth row of an
-// off-diagonal block's first group) against the 5 rows at `b`; kind 2: the 5-cycle of the group at `b`
-// walked in the order given by perm (as the third part of sweep_comp); kind 0: nothing.
-struct HelpUnits {
-  int kind[3];
-  int a[3], b[3];      // shared-memory offsets (floats) inside a stage
-  int perm[3];
-};
-template <int T>
-__device__ __forceinline__ void sweep_help(const float* buf, const HelpUnits& hu, int lane, u64 (&acc)[kRSlots]) {
-#pragma unroll
-  for (int c = 0; c < T; c += 128) {
-    const int o = c + lane * 4;
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      if (hu.kind[q] == 1) {
-        const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(buf + hu.a[q] + o);
-#pragma unroll
-        for (int j = 0; j < kG; ++j) {
-          const ulonglong2 r = *reinterpret_cast<const ulonglong2*>(buf + hu.b[q] + j * T + o);
-          const u64 d0 = sub2(x.x, r.x), d1 = sub2(x.y, r.y);
-          acc[q * kG + j] = fma2(d0, d0, acc[q * kG + j]);
-          acc[q * kG + j] = fma2(d1, d1, acc[q * kG + j]);
-        }
-      } else if (hu.kind[q] == 2) {
-        u64 a0[kG], a1[kG];
-#pragma unroll
-        for (int i = 0; i < kG; ++i) {
-          const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(buf + hu.b[q] + zperm(i, hu.perm[q]) * T + o);
-          a0[i] = t.x; a1[i] = t.y;
-        }
-#pragma unroll
-        for (int e = 0; e < kG; ++e) {
-          const int i = (e < 4) ? e : 0, j = (e < 4) ? e + 1 : 4;
-          const u64 d0 = sub2(a0[i], a0[j]), d1 = sub2(a1[i], a1[j]);
-          acc[q * kG + e] = fma2(d0, d0, acc[q * kG + e]);
-          acc[q * kG + e] = fma2(d1, d1, acc[q * kG + e]);
-        }
-      }
-    }
-  }
-}
-
 // STAR: the pivot row against NS consecutive rows (NS = 3: a new row's pairs spread over many warps, so
 // that a reuse pass is bound by the staging of the rows, not by one warp's 25 pairs; NS = 25 when there
 // are too few warps for that).  Each pair goes through exactly the operations it goes through in an
@@ -444,31 +345,8 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
   const int cluster_id = CLUSTER ? (int)(blockIdx.x / C) : (int)blockIdx.x;
   const int nclusters = CLUSTER ? (int)(gridDim.x / C) : (int)gridDim.x;
 
-  // split shape: one 16-warp CTA for the 12 tasks of 21 <= n <= 25 (see sweep_off4 / sweep_help)
-  constexpr bool SPLIT = (W == kRWarpsWide) && !CLUSTER;
   Task task;
-  HelpUnits hu = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-  int hg0[3] = {-1, -1, -1}, hg1[3] = {-1, -1, -1};      // helper units: the groups they belong to (write-out)
-  if (SPLIT && star.count == 0) {
-    if (warp < kRWarps) {
-      task = make_task(warp, ng);
-      if (task.kind == 1) task.kind = 4;                  // the 4 x 5 part
-      else if (task.kind == 2) task.kind = 5;             // the two whole diagonals
-    } else {
-      task = Task{6, -1, -1, -1, 0};
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const Task t = make_task((warp - kRWarps) * 3 + q, ng);
-        if (t.kind == 1) {
-          hu.kind[q] = 1; hu.a[q] = (t.g0 * kG + kG - 1) * T; hu.b[q] = t.g1 * kG * T;
-          hg0[q] = t.g0; hg1[q] = t.g1;
-        } else if (t.kind == 2 && t.g2 >= 0) {
-          hu.kind[q] = 2; hu.b[q] = t.g2 * kG * T; hu.perm[q] = t.perm;
-          hg0[q] = t.g2;
-        }
-      }
-    }
-  } else if (star.count == 0) {
+  if (star.count == 0) {
     task = make_task(rank * W + warp, ng);
   } else {
     // reuse call: star task t = (new row t / chunks, rows [slots (t % chunks), + slots)); g1 = first ROW here
@@ -563,11 +441,8 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
   for (int k = 0; k < mine; ++k) {
     mbar_wait(&full[s], parity);
     const float* buf = stages + (size_t)s * stage_floats;
-    if (SPLIT && task.kind == 4)      sweep_off4<T>(buf + o0, buf + o1, lane, acc);
-    else if (SPLIT && task.kind == 5) sweep_diag2<T>(buf + o0, buf + o1, lane, acc);
-    else if (SPLIT && task.kind == 6) sweep_help<T>(buf, hu, lane, acc);
-    else if (!SPLIT && task.kind == 1) sweep_off<T>(buf + o0, buf + o1, lane, acc);
-    else if (!SPLIT && task.kind == 2) sweep_comp<T>(buf + o0, buf + o1, buf + o2, task.perm, lane, acc);
+    if (task.kind == 1)      sweep_off<T>(buf + o0, buf + o1, lane, acc);
+    else if (task.kind == 2) sweep_comp<T>(buf + o0, buf + o1, buf + o2, task.perm, lane, acc);
     else if (task.kind == 3) {
       if (star.slots == 3) sweep_star<T, 3>(buf + o0, buf + o1, star_valid, lane, acc);
       else                 sweep_star<T, kRSlots>(buf + o0, buf + o1, star_valid, lane, acc);
@@ -601,11 +476,8 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    if (SPLIT && task.kind == 4)      sweep_off4<T>(stages + o0, stages + o1, lane, acc);
-    else if (SPLIT && task.kind == 5) sweep_diag2<T>(stages + o0, stages + o1, lane, acc);
-    else if (SPLIT && task.kind == 6) sweep_help<T>(stages, hu, lane, acc);
-    else if (!SPLIT && task.kind == 1) sweep_off<T>(stages + o0, stages + o1, lane, acc);
-    else if (!SPLIT && task.kind == 2) sweep_comp<T>(stages + o0, stages + o1, stages + o2, task.perm, lane, acc);
+    if (task.kind == 1)      sweep_off<T>(stages + o0, stages + o1, lane, acc);
+    else if (task.kind == 2) sweep_comp<T>(stages + o0, stages + o1, stages + o2, task.perm, lane, acc);
     else if (task.kind == 3) {
       if (star.slots == 3) sweep_star<T, 3>(stages + o0, stages + o1, star_valid, lane, acc);
       else                 sweep_star<T, kRSlots>(stages + o0, stages + o1, star_valid, lane, acc);
@@ -616,39 +488,7 @@ k2_ring(const __grid_constant__ RowTable rows, const __grid_constant__ SelfList 
   if (task.kind != 0 && pending > 0) ring_flush(acc, lane, dacc);
 
   double* block = parts + (size_t)cluster_id * n * n;
-  if (SPLIT && task.kind == 4) {
-    const int i = lane / kG, j = lane % kG;
-    const int ri = task.g0 * kG + i, rj = task.g1 * kG + j;
-    if (lane < (kG - 1) * kG && ri < n && rj < n) block[(size_t)ri * n + rj] = dacc;
-  } else if (SPLIT && task.kind == 5) {
-    if (lane < 20) {
-      const int p = lane < 10 ? lane : lane - 10;
-      const int g = lane < 10 ? task.g0 : task.g1;
-      const int i = (p >= 9) ? 3 : (p >= 7) ? 2 : (p >= 4) ? 1 : 0;
-      const int first = (i == 0) ? 0 : (i == 1) ? 4 : (i == 2) ? 7 : 9;
-      const int j = p - first + i + 1;
-      if (g >= 0) {
-        const int ri = g * kG + i, rj = g * kG + j;
-        if (ri < n && rj < n) block[(size_t)ri * n + rj] = dacc;
-      }
-    }
-  } else if (SPLIT && task.kind == 6) {
-    if (lane < 3 * kG) {
-      const int q = lane / kG, e = lane % kG;
-      const int kindq = q == 0 ? hu.kind[0] : q == 1 ? hu.kind[1] : hu.kind[2];
-      const int g0q = q == 0 ? hg0[0] : q == 1 ? hg0[1] : hg0[2];
-      const int g1q = q == 0 ? hg1[0] : q == 1 ? hg1[1] : hg1[2];
-      const int permq = q == 0 ? hu.perm[0] : q == 1 ? hu.perm[1] : hu.perm[2];
-      if (kindq == 1) {
-        const int ri = g0q * kG + kG - 1, rj = g1q * kG + e;
-        if (ri < n && rj < n) block[(size_t)ri * n + rj] = dacc;
-      } else if (kindq == 2) {
-        const int a = zperm((e < 4) ? e : 0, permq), b = zperm((e < 4) ? e + 1 : 4, permq);
-        const int ri = g0q * kG + min(a, b), rj = g0q * kG + max(a, b);
-        if (ri < n && rj < n) block[(size_t)ri * n + rj] = dacc;
-      }
-    }
-  } else if (task.kind == 1) {
+  if (task.kind == 1) {
     const int i = lane / kG, j = lane % kG;
     const int ri = task.g0 * kG + i, rj = task.g1 * kG + j;
     if (lane < kRSlots && ri < n && rj < n) block[(size_t)ri * n + rj] = dacc;
@@ -869,11 +709,9 @@ static bool ring_shape(int n, int& W, int& C) {
   static const bool w12 = [] { const char* e = getenv("BYZAGG_K2_W12"); return e && e[0] == '1'; }();
   static const bool w16 = [] { const char* e = getenv("BYZAGG_K2_W16"); return !(e && e[0] == '0'); }();
   const int ng = (n + kG - 1) / kG, tasks = ring_ntasks(ng);
-  static const bool split = [] { const char* e = getenv("BYZAGG_K2_SPLIT"); return e && e[0] == '1'; }();
   W = kRWarps;
   if (tasks <= kRWarpsSmall && n <= 3 * kRWarpsSmall && !w12) W = kRWarpsSmall;
   else if (ng * kG > 35 && w16) W = kRWarpsWide;
-  else if (ng == 5 && split) { W = kRWarpsWide; C = 1; return true; }      // split shape: 16 warps share the 12 tasks
   C = (tasks + W - 1) / W;
   if (C < 1) C = 1;
   return C <= kRMaxCluster;
@@ -961,8 +799,6 @@ int launch_pairdist_ring(const RowTable& rows, int n, int64_t d, double* parts, 
     if (rows_alloc > 25) return -1;
     if (W == kRWarpsSmall) nparts = selfk ? launch_ring_cfg<512, 3, true, false, kRWarpsSmall>(rows, self, tail, star, n, C, d, parts, st)
                                           : launch_ring_cfg<512, 3, false, false, kRWarpsSmall>(rows, self, tail, star, n, C, d, parts, st);
-    else if (W == kRWarpsWide) nparts = selfk ? launch_ring_cfg<512, 4, true, false, kRWarpsWide>(rows, self, tail, star, n, C, d, parts, st)
-                                              : launch_ring_cfg<512, 4, false, false, kRWarpsWide>(rows, self, tail, star, n, C, d, parts, st);
     else                   nparts = BZ_RING(512, 4, false);
   } else if (rows_alloc <= 35) nparts = BZ_RING(512, 3, true);
   else if (W == kRWarpsWide)   nparts = selfk ? launch_ring_cfg<256, 3, true, true, kRWarpsWide>(rows, self, tail, star, n, C, d, parts, st)

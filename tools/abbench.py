@@ -39,9 +39,6 @@ def main():
   libs = [a for a in sys.argv[1:] if not a.startswith("--")]
   if "--dist" in sys.argv:      # the distance-based rules (K2 experiments)
     cases = [("krum", 25, 5, 1310922), ("bulyan", 25, 5, 1310922), ("krum", 25, 5, 36489290), ("cge", 25, 5, 1310922), ("krum", 51, 12, 1310922)]
-  elif "--split" in sys.argv:   # 16 warps sharing the 12 tasks of n = 21..25
-    cases = [("krum", 25, 5, 1310922), ("bulyan", 25, 5, 1310922), ("krum", 25, 10, 1310922), ("krum", 25, 5, 36489290), ("krum", 21, 4, 1310922),
-             ("krum", 25, 5, 79510), ("krum", 25, 5, 8388608)]
   elif "--wide" in sys.argv:    # clusters of 16-warp CTAs (n > 35)
     cases = [("krum", 51, 12, 4568373), ("bulyan", 51, 12, 4568373), ("krum", 51, 12, 1310922), ("krum", 40, 9, 1310922), ("krum", 45, 10, 1310922),
              ("krum", 64, 15, 1310922), ("krum", 51, 12, 36546980), ("krum", 35, 8, 1310922)]
