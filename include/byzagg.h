@@ -94,7 +94,7 @@ BZ_API int bz_meamed(const float* const* rows, int n, int f, int64_t d, float* o
  *   staging     DEVICE fp32[n][pitch] scratch (pitch >= d, multiple of 4; 64 keeps 256-byte row alignment)
  *   dev_out     DEVICE fp32[d] scratch
  *   in_stream / out_stream  copy streams (may equal `stream`: then everything is serial) */
-/* Staging alone (any rule): n HOST rows -> DEVICE staging[k][pitch], as one batched copy when the driver
+/* Staging alone (any rule; the same `--device-gar` hop, attack.py:811-815): n HOST rows -> DEVICE staging[k][pitch], as one batched copy when the driver
  * has cudaMemcpyBatchAsync and `stream` is not the legacy default stream, else n cudaMemcpyAsync. */
 BZ_API int bz_stage_rows(const float* const* host_rows, int n, int64_t d, float* staging, int64_t pitch, void* stream);
 #define BZ_RULE_AVERAGE 0
