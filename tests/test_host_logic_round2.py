@@ -84,3 +84,51 @@ def test_shard_bounds_cover_the_vector_without_overlap():
     assert spans[0][0] == 0 and spans[-1][1] == d
     assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
     assert all(lo <= hi for lo, hi in spans)
+
+def test_study_step_bookkeeping_with_the_device_passes_replaced(monkeypatch):
+  """ engine.study_step: which dot product lands in which cosine (attack.py:854-866), NaN columns without
+  attack gradients, the curvature sum over the past gradients — checked on the CPU by replacing the two
+  device passes (K6 and bz_rowdots) with plain tensor code.  (The CUDA passes themselves: -m gpu tests.) """
+  import math
+  def fake_avg_dev_max(samples):
+    stack = torch.stack(samples).double()
+    avg = stack.mean(dim=0)
+    stats = torch.cat([avg.pow(2).sum().reshape(1), avg.abs().max().reshape(1), (stack - avg).pow(2).sum(dim=1)])
+    return avg.float(), stats
+  def fake_rowdots(center, rows):
+    return torch.stack([torch.dot(r.double(), center.double()) for r in rows])
+  monkeypatch.setattr(engine, "avg_dev_max_async", fake_avg_dev_max)
+  monkeypatch.setattr(engine, "rowdots_async", fake_rowdots)
+  gen = torch.Generator().manual_seed(5)
+  d = 97
+  for ns, nh, na, npast, shared in [(6, 6, 2, 2, True), (6, 4, 0, 3, False), (3, 3, 1, 0, False)]:
+    sampleds = [torch.randn(d, generator=gen) for _ in range(ns)]
+    honests = sampleds[:nh] if shared else [torch.randn(d, generator=gen) for _ in range(nh)]
+    attacks = [torch.randn(d, generator=gen) for _ in range(na)]
+    defense = torch.randn(d, generator=gen)
+    pasts = [(g, g.norm().item()) for g in (torch.randn(d, generator=gen) for _ in range(npast))]
+    got = engine.study_step(sampleds, honests, attacks, defense, pasts, 0.9)
+    s_avg = torch.stack(sampleds).double().mean(dim=0)
+    h_avg = torch.stack(honests).double().mean(dim=0)
+    a_avg = torch.stack(attacks).double().mean(dim=0) if na else None
+    dd = defense.double()
+    cos = lambda a, b: math.nan if a is None or b is None else (torch.dot(a, b) / a.norm() / b.norm()).item()
+    want = dict(cosin_splhon=cos(s_avg, h_avg), cosin_splatt=cos(s_avg, a_avg), cosin_spldef=cos(s_avg, dd),
+                cosin_honatt=cos(h_avg, a_avg), cosin_hondef=cos(h_avg, dd), cosin_attdef=cos(a_avg, dd),
+                sampled_norm_avg=s_avg.norm().item(), honest_norm_avg=h_avg.norm().item(), defense_norm_avg=dd.norm().item(),
+                defense_norm_max=dd.abs().max().item(),
+                sampled_norm_dev=math.sqrt(sum((g.double() - s_avg).pow(2).sum().item() for g in sampleds) / (ns - 1)),
+                attack_norm_avg=a_avg.norm().item() if na else math.nan,
+                attack_norm_dev=(math.sqrt(sum((g.double() - a_avg).pow(2).sum().item() for g in attacks) / (na - 1)) if na > 1 else math.nan))
+    if npast:
+      want["cosin_sampled"] = (torch.dot(s_avg, pasts[0][0].double()) / s_avg.norm() / pasts[0][1]).item()
+      want["curv_sampled"] = 0.9 * sum(0.9 ** i * torch.dot(s_avg, g.double()).item() for i, (g, _) in enumerate(pasts))
+    else:
+      want["cosin_sampled"] = want["curv_sampled"] = math.nan
+    for key, ref in want.items():
+      if math.isnan(ref):
+        assert math.isnan(got[key]), (key, got[key])
+      else:
+        assert abs(got[key] - ref) <= 1e-5 * abs(ref) + 1e-6, (key, got[key], ref)
+    assert (got["attack_grad_avg"] is None) == (na == 0)
+    assert torch.allclose(got["sampled_grad_avg"].double(), s_avg, atol=1e-6)
