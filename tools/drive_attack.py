@@ -134,6 +134,15 @@ def run_attack(path, fuse, helper, fuse_study=False):
   exec(compile(source, str(path), "exec"), scope)
   return scope
 
+def find_reference(root):
+  """ $BYZ_REFERENCE, <repo>/baseline/_ref (tools/install_ref.sh), /root/reference: the first that holds attack.py. """
+  import os
+  places = ([pathlib.Path(os.environ["BYZ_REFERENCE"])] if os.environ.get("BYZ_REFERENCE") else []) + [root / "baseline" / "_ref", pathlib.Path("/root/reference")]
+  for path in places:
+    if (path / "aggregators" / "__init__.py").exists() and (path / "attack.py").exists():
+      return path.resolve()
+  return None
+
 def main():
   parser = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
   parser.add_argument("--reference", default=None, help="root of the ByzantineMomentum checkout (default: $BYZ_REFERENCE, baseline/_ref, /root/reference)")
@@ -152,8 +161,7 @@ def main():
   root = pathlib.Path(__file__).resolve().parent.parent
   sys.path.insert(0, str(root))
   if args.reference is None:
-    from oracle import reference as refloc      # locating only: the run below is the reference's own code
-    ref = refloc.find_root()
+    ref = find_reference(root)
     if ref is None:
       raise SystemExit("no reference found (run tools/install_ref.sh or pass --reference)")
   else:

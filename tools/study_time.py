@@ -54,8 +54,9 @@ def main():
   pasts = [(g, g.norm().item()) for g in (torch.randn(d, device=dev) for _ in range(npast))]
   stock = library_avg_dev_max
   try:
-    from oracle import reference as refloc      # locating only
-    ref = refloc.find_root()
+    import os
+    places = ([pathlib.Path(os.environ["BYZ_REFERENCE"])] if os.environ.get("BYZ_REFERENCE") else []) + [ROOT / "baseline" / "_ref", pathlib.Path("/root/reference")]
+    ref = next((q.resolve() for q in places if (q / "tools" / "__init__.py").exists() and (q / "attack.py").exists()), None)
     if ref is not None:
       sys.path.insert(0, str(ref))
       import tools as reftools
