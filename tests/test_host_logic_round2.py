@@ -132,3 +132,16 @@ def test_study_step_bookkeeping_with_the_device_passes_replaced(monkeypatch):
         assert abs(got[key] - ref) <= 1e-5 * abs(ref) + 1e-6, (key, got[key], ref)
     assert (got["attack_grad_avg"] is None) == (na == 0)
     assert torch.allclose(got["sampled_grad_avg"].double(), s_avg, atol=1e-6)
+
+def test_nothing_outside_tests_smoke_and_bench_imports_the_oracle():
+  """ oracle/ is the checker: the product (`byzantinemomentum_b200/`, `native/`) and the helper scripts
+  (`tools/`) must not import it; `bench.py` and `__graft_entry__.py` may (CPU legs / smoke check). """
+  import pathlib, re
+  root = pathlib.Path(__file__).resolve().parent.parent
+  pattern = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)", re.M)
+  offenders = []
+  for folder in ("byzantinemomentum_b200", "native", "tools"):
+    for path in (root / folder).rglob("*.py"):
+      if pattern.search(path.read_text()):
+        offenders.append(str(path.relative_to(root)))
+  assert offenders == []
